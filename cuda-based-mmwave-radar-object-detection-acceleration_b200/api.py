@@ -1,0 +1,332 @@
+"""ctypes binding of libmmw_radar_b200.so — the only compute path of this package.
+
+There is no Python/numpy/torch implementation of any stage here: every call goes through the
+C ABI of include/mmw_radar.h / include/mmw_legacy.h into the CUDA kernels, and raises if the
+library is missing or a CUDA call fails.  torch is used by callers only for device buffers,
+streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MMW_OK, MMW_ERR_ARG, MMW_ERR_CUDA, MMW_ERR_STATE, MMW_ERR_OVERFLOW = 0, -1, -2, -3, -4
+FLAG_PEAK = 1
+
+DET_DTYPE = np.dtype(
+    [
+        ("frame", "<u4"),
+        ("range_bin", "<u2"),
+        ("doppler_bin", "<u2"),
+        ("power", "<f4"),
+        ("noise", "<f4"),
+        ("angle_bin", "<i2"),
+        ("flags", "<u2"),
+        ("angle_rad", "<f4"),
+    ]
+)
+assert DET_DTYPE.itemsize == 24
+
+# every symbol include/mmw_radar.h and include/mmw_legacy.h declare
+C_ABI_SYMBOLS = [
+    "mmw_default_config", "mmw_create", "mmw_destroy", "mmw_last_error", "mmw_get_info",
+    "mmw_set_windows", "mmw_get_windows", "mmw_set_frame_offset", "mmw_stream", "mmw_use_stream",
+    "mmw_process_device", "mmw_process_host", "mmw_read_detections", "mmw_read_counts",
+    "mmw_device_results", "mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map",
+    "mmw_copy_cfar_mask", "mmw_time_device",
+    "mmw_legacy_process_frame", "mmw_legacy_process_frames", "mmw_legacy_copy_spectrum", "mmw_legacy_shutdown",
+]
+# the reference's own entry point (acceleration.h:32), C++ linkage
+LEGACY_MANGLED = "_Z14cudaProcessingPsP9Complex_tiPdS2_S2_S2_"
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("n_samples", C.c_int), ("n_chirps", C.c_int), ("n_antennas", C.c_int), ("max_frames", C.c_int),
+        ("cfar_guard_r", C.c_int), ("cfar_guard_d", C.c_int), ("cfar_train_r", C.c_int), ("cfar_train_d", C.c_int),
+        ("cfar_alpha", C.c_float), ("max_det_per_frame", C.c_int), ("keep_doppler_cube", C.c_int),
+        ("lambda_over_d", C.c_float), ("device", C.c_int),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("Sp", C.c_int), ("Cp", C.c_int), ("n_theta", C.c_int), ("sm_count", C.c_int),
+        ("adc_bytes_per_frame", C.c_longlong), ("algorithmic_bytes_per_frame", C.c_longlong),
+        ("workspace_bytes", C.c_longlong), ("kernels_per_batch", C.c_int),
+    ]
+
+
+class RadarError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mmw error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Loads the shared library (building it with nvcc if it is absent or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError(f"{_build.LIB} is missing: the CUDA library was not built; there is no fallback path")
+    L = C.CDLL(_build.LIB)
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    L.mmw_last_error.restype = C.c_char_p
+    L.mmw_default_config.argtypes = [C.POINTER(Config), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mmw_default_config.restype = None
+    L.mmw_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.mmw_destroy.argtypes = [vp]
+    L.mmw_destroy.restype = None
+    L.mmw_get_info.argtypes = [vp, C.POINTER(Info)]
+    L.mmw_set_windows.argtypes = [vp, vp, vp]
+    L.mmw_get_windows.argtypes = [vp, vp, vp]
+    L.mmw_set_frame_offset.argtypes = [vp, C.c_uint32]
+    L.mmw_stream.argtypes = [vp]
+    L.mmw_stream.restype = vp
+    L.mmw_use_stream.argtypes = [vp, vp]
+    L.mmw_process_device.argtypes = [vp, vp, C.c_int]
+    L.mmw_process_host.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip]
+    L.mmw_read_detections.argtypes = [vp, vp, C.c_int, ip]
+    L.mmw_read_counts.argtypes = [vp, vp, C.c_int]
+    L.mmw_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    for name in ("mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map", "mmw_copy_cfar_mask"):
+        getattr(L, name).argtypes = [vp, C.c_int, vp]
+    L.mmw_time_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.mmw_legacy_process_frame.argtypes = [vp, vp, C.c_int, ip]
+    L.mmw_legacy_process_frame.restype = C.c_double
+    L.mmw_legacy_process_frames.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+    L.mmw_legacy_copy_spectrum.argtypes = [vp]
+    L.mmw_legacy_shutdown.restype = None
+    cp = getattr(L, LEGACY_MANGLED)
+    cp.restype = C.c_double
+    cp.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int, allow_overflow: bool = False) -> int:
+    if rc == MMW_OK or (allow_overflow and rc == MMW_ERR_OVERFLOW):
+        return rc
+    raise RadarError(rc, load().mmw_last_error().decode(errors="replace"))
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t) -> int:
+    """Accepts a torch CUDA tensor or a raw integer device address."""
+    if isinstance(t, int):
+        return t
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return t.data_ptr()
+
+
+def next_pow2(n: int) -> int:
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+class RadarContext:
+    """One plan + HBM workspace on one GPU (mmw_ctx).  Mirrors what cudaProcessing()
+    (acceleration.cu:417-572) allocates per frame, held once for a batch of `max_frames` frames."""
+
+    def __init__(self, n_samples: int, n_chirps: int, n_antennas: int, max_frames: int, *,
+                 cfar_guard=(2, 2), cfar_train=(8, 4), cfar_alpha: float = 15.0, max_det_per_frame: int = 1024,
+                 keep_doppler_cube: bool = False, lambda_over_d: float = 2.0, device: int = -1):
+        self._L = load()
+        cfg = Config()
+        self._L.mmw_default_config(C.byref(cfg), n_samples, n_chirps, n_antennas, max_frames)
+        cfg.cfar_guard_r, cfg.cfar_guard_d = cfar_guard
+        cfg.cfar_train_r, cfg.cfar_train_d = cfar_train
+        cfg.cfar_alpha = cfar_alpha
+        cfg.max_det_per_frame = max_det_per_frame
+        cfg.keep_doppler_cube = int(keep_doppler_cube)
+        cfg.lambda_over_d = lambda_over_d
+        cfg.device = device
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        _check(self._L.mmw_create(C.byref(cfg), C.byref(self._h)))
+        info = Info()
+        _check(self._L.mmw_get_info(self._h, C.byref(info)))
+        self.info = info
+        self.S, self.C, self.A = n_samples, n_chirps, n_antennas
+        self.Sp, self.Cp, self.n_theta = info.Sp, info.Cp, info.n_theta
+        self.max_frames = max_frames
+        self.max_det_per_frame = max_det_per_frame
+        self.frame_shorts = 2 * n_samples * n_chirps * n_antennas
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.mmw_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration
+    def set_windows(self, win_range=None, win_doppler=None):
+        wr = None if win_range is None else np.ascontiguousarray(win_range, np.float32)
+        wd = None if win_doppler is None else np.ascontiguousarray(win_doppler, np.float32)
+        if wr is not None and wr.size != self.S:
+            raise ValueError("range window must have n_samples entries")
+        if wd is not None and wd.size != self.C:
+            raise ValueError("doppler window must have n_chirps entries")
+        _check(self._L.mmw_set_windows(self._h, None if wr is None else _np_ptr(wr), None if wd is None else _np_ptr(wd)))
+
+    def get_windows(self):
+        wr = np.empty(self.S, np.float32)
+        wd = np.empty(self.C, np.float32)
+        _check(self._L.mmw_get_windows(self._h, _np_ptr(wr), _np_ptr(wd)))
+        return wr, wd
+
+    def set_frame_offset(self, first_frame: int):
+        _check(self._L.mmw_set_frame_offset(self._h, int(first_frame)))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.mmw_stream(self._h) or 0)
+
+    def use_stream(self, cuda_stream: int | None):
+        _check(self._L.mmw_use_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    # -- processing
+    def process_device(self, adc_dev, n_frames: int):
+        """adc_dev: torch int16 CUDA tensor (or device address) of n_frames captures; asynchronous."""
+        _check(self._L.mmw_process_device(self._h, C.c_void_p(_dev_ptr(adc_dev)), n_frames))
+
+    def process_host(self, adc_host, n_frames: int, det_capacity: int | None = None, out: np.ndarray | None = None):
+        """adc_host: numpy int16 array or a (pinned) CPU torch tensor. Returns (detections, overflow_flag)."""
+        if isinstance(adc_host, np.ndarray):
+            a = np.ascontiguousarray(adc_host, np.int16)
+            ptr, n = a.ctypes.data, a.size
+        else:
+            ptr, n = adc_host.data_ptr(), adc_host.numel()
+        if n < n_frames * self.frame_shorts:
+            raise ValueError("capture buffer shorter than n_frames frames")
+        cap = det_capacity if det_capacity is not None else n_frames * self.max_det_per_frame
+        dets = out if out is not None else np.empty(cap, DET_DTYPE)
+        cap = min(cap, dets.size)
+        n_det = C.c_int(0)
+        rc = _check(self._L.mmw_process_host(self._h, C.c_void_p(ptr), n_frames, _np_ptr(dets), cap, C.byref(n_det)), True)
+        return dets[: n_det.value], rc == MMW_ERR_OVERFLOW
+
+    def read_detections(self, det_capacity: int | None = None):
+        cap = det_capacity if det_capacity is not None else self.max_frames * self.max_det_per_frame
+        dets = np.empty(cap, DET_DTYPE)
+        n_det = C.c_int(0)
+        rc = _check(self._L.mmw_read_detections(self._h, _np_ptr(dets), cap, C.byref(n_det)), True)
+        return dets[: n_det.value].copy(), rc == MMW_ERR_OVERFLOW
+
+    def read_counts(self, n_frames: int) -> np.ndarray:
+        counts = np.empty(n_frames, np.uint32)
+        _check(self._L.mmw_read_counts(self._h, _np_ptr(counts), n_frames))
+        return counts
+
+    def device_results(self):
+        """(device address of the dense ordered detection list, device address of the 4-word header)."""
+        d, h = C.c_void_p(), C.c_void_p()
+        _check(self._L.mmw_device_results(self._h, C.byref(d), C.byref(h)))
+        return int(d.value), int(h.value)
+
+    # -- intermediates (canonical layouts)
+    def range_spectrum(self, frame: int) -> np.ndarray:
+        out = np.empty((self.A, self.Sp, self.C), np.complex64)
+        _check(self._L.mmw_copy_range_spectrum(self._h, frame, _np_ptr(out)))
+        return out
+
+    def doppler_cube(self, frame: int) -> np.ndarray:
+        out = np.empty((self.A, self.Sp, self.Cp), np.complex64)
+        _check(self._L.mmw_copy_doppler_cube(self._h, frame, _np_ptr(out)))
+        return out
+
+    def power_map(self, frame: int) -> np.ndarray:
+        out = np.empty((self.Sp, self.Cp), np.float32)
+        _check(self._L.mmw_copy_power_map(self._h, frame, _np_ptr(out)))
+        return out
+
+    def cfar_mask(self, frame: int) -> np.ndarray:
+        out = np.empty((self.Sp, self.Cp), np.uint8)
+        _check(self._L.mmw_copy_cfar_mask(self._h, frame, _np_ptr(out)))
+        return out
+
+    # -- timing
+    def time_device(self, adc_dev, n_frames: int, iters: int, per_stage: bool = False):
+        total = C.c_float(0)
+        stages = (C.c_float * 4)()
+        _check(self._L.mmw_time_device(self._h, C.c_void_p(_dev_ptr(adc_dev)), n_frames, iters, C.byref(total),
+                                       stages if per_stage else None))
+        return (total.value, list(stages)) if per_stage else total.value
+
+
+# ---------------------------------------------------------------------------
+# legacy entry point (reference cfg: 100 x 128 x 4)
+# ---------------------------------------------------------------------------
+def cudaProcessing(frame: np.ndarray, base_frame_rx0: np.ndarray, size: int | None = None, timers: np.ndarray | None = None) -> float:
+    """Calls the C++-linkage drop-in symbol exactly as the reference's cudaTiming() does
+    (cudaBenchMarking.cpp:377). timers = float64[4] (fft, preProcess, findMax, total), accumulated."""
+    L = load()
+    frame = np.ascontiguousarray(frame, np.int16)
+    base = np.ascontiguousarray(base_frame_rx0, np.complex128)
+    if base.size != 12800:
+        raise ValueError("base frame must hold 12800 complex values (rx0 of frame 0)")
+    t = timers if timers is not None else np.zeros(4, np.float64)
+    fn = getattr(L, LEGACY_MANGLED)
+    p = t.ctypes.data
+    return fn(_np_ptr(frame), _np_ptr(base), frame.size if size is None else size,
+              C.c_void_p(p), C.c_void_p(p + 8), C.c_void_p(p + 16), C.c_void_p(p + 24))
+
+
+def legacy_process_frame(frame: np.ndarray, base_frame_rx0: np.ndarray, size: int | None = None):
+    L = load()
+    frame = np.ascontiguousarray(frame, np.int16)
+    base = np.ascontiguousarray(base_frame_rx0, np.complex128)
+    raw = C.c_int(0)
+    d = L.mmw_legacy_process_frame(_np_ptr(frame), _np_ptr(base), frame.size if size is None else size, C.byref(raw))
+    if d < 0:
+        raise RadarError(int(d), L.mmw_last_error().decode(errors="replace"))
+    return d, raw.value
+
+
+def legacy_process_frames(frames: np.ndarray, base_frame_rx0: np.ndarray):
+    L = load()
+    frames = np.ascontiguousarray(frames, np.int16)
+    base = np.ascontiguousarray(base_frame_rx0, np.complex128)
+    n = frames.shape[0]
+    dist = np.empty(n, np.float64)
+    raw = np.empty(n, np.int32)
+    _check(L.mmw_legacy_process_frames(_np_ptr(frames), n, _np_ptr(base), frames.shape[1], _np_ptr(dist), _np_ptr(raw)))
+    return dist, raw
+
+
+def legacy_spectrum() -> np.ndarray:
+    out = np.empty(16384, np.complex64)
+    _check(load().mmw_legacy_copy_spectrum(_np_ptr(out)))
+    return out

@@ -1,0 +1,487 @@
+// mmw_api.cu — host side of the C ABI declared in include/mmw_radar.h: context, plan tables,
+// HBM workspace, stream, and the launch sequence of one batch.  No torch types, no CPU compute
+// path: every processing call either launches the CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "mmw_common.cuh"
+
+namespace mmw {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int next_pow2(int n)
+{
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+}  // namespace mmw
+
+using namespace mmw;
+
+struct mmw_ctx {
+    mmw_config cfg;
+    PlanDev plan;
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    // tables
+    float *d_win_r, *d_win_d;
+    float2 *d_tw_r, *d_tw_d, *d_tw_a;
+    // workspace
+    int16_t *d_adc;          // staging for host captures
+    float2 *d_rs;
+    float2 *d_cube;
+    float *d_pmap;
+    uint32_t *d_mask;
+    mmw_detection *d_dets;
+    uint32_t *d_counts;
+    mmw_detection *d_dense;
+    uint32_t *d_header;
+    void *d_scratch;         // export scratch
+    size_t scratch_bytes;
+    // pinned host
+    uint32_t *h_header;
+    mmw_detection *h_dense;
+    int dense_cap;
+    int last_frames;
+    size_t workspace_bytes;
+    cudaEvent_t ev[6];
+};
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            set_last_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return MMW_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(mmw_ctx *c, T **p, size_t count)
+{
+    const size_t bytes = count * sizeof(T);
+    CK(cudaMalloc((void **)p, bytes ? bytes : 16));
+    c->workspace_bytes += bytes;
+    return MMW_OK;
+}
+
+static std::vector<float2> make_twiddles(int n)
+{
+    std::vector<float2> t(n);
+    for (int k = 0; k < n; ++k) {
+        const double th = -2.0 * M_PI * (double)k / (double)n;
+        t[k] = make_float2((float)cos(th), (float)sin(th));
+    }
+    return t;
+}
+
+static std::vector<float> make_hann(int n)
+{
+    std::vector<float> w(n);
+    for (int i = 0; i < n; ++i) w[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)i / (double)n));
+    return w;
+}
+
+extern "C" {
+
+const char *mmw_last_error(void) { return g_err; }
+
+void mmw_default_config(mmw_config *cfg, int n_samples, int n_chirps, int n_antennas, int max_frames)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->n_samples = n_samples;
+    cfg->n_chirps = n_chirps;
+    cfg->n_antennas = n_antennas;
+    cfg->max_frames = max_frames;
+    cfg->cfar_guard_r = 2;
+    cfg->cfar_guard_d = 2;
+    cfg->cfar_train_r = 8;
+    cfg->cfar_train_d = 4;
+    cfg->cfar_alpha = 15.0f;
+    cfg->max_det_per_frame = 1024;
+    cfg->keep_doppler_cube = 0;
+    cfg->lambda_over_d = 2.0f;
+    cfg->device = -1;
+}
+
+void mmw_destroy(mmw_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw_r); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
+    cudaFree(c->d_adc); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_mask);
+    cudaFree(c->d_dets); cudaFree(c->d_counts); cudaFree(c->d_dense); cudaFree(c->d_header); cudaFree(c->d_scratch);
+    if (c->h_header) cudaFreeHost(c->h_header);
+    if (c->h_dense) cudaFreeHost(c->h_dense);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int mmw_create(const mmw_config *cfg, mmw_ctx **out)
+{
+    if (!cfg || !out) { set_last_error("mmw_create: null argument"); return MMW_ERR_ARG; }
+    *out = nullptr;
+    const int S = cfg->n_samples, C = cfg->n_chirps, A = cfg->n_antennas;
+    if (S < 4 || (S % 4) != 0) { set_last_error("n_samples must be a positive multiple of 4 (IIQQ packing + 16-byte rows), got %d", S); return MMW_ERR_ARG; }
+    if (C < 2 || (C % 2) != 0) { set_last_error("n_chirps must be a positive multiple of 2, got %d", C); return MMW_ERR_ARG; }
+    if (A < 1 || A > 256) { set_last_error("n_antennas must be 1..256, got %d", A); return MMW_ERR_ARG; }
+    if (cfg->max_frames < 1) { set_last_error("max_frames must be >= 1"); return MMW_ERR_ARG; }
+    const int Sp = next_pow2(S), Cp = next_pow2(C);
+    const char *why = nullptr;
+    if (!plan_supported(Sp, Cp, &why)) { set_last_error("unsupported shape: %s", why); return MMW_ERR_ARG; }
+    const int Gr = cfg->cfar_guard_r, Gd = cfg->cfar_guard_d, Tr = cfg->cfar_train_r, Td = cfg->cfar_train_d;
+    if (Gr < 0 || Gd < 0 || Tr < 0 || Td < 0 || Tr + Td == 0) { set_last_error("bad CFAR window"); return MMW_ERR_ARG; }
+    if (2 * (Gd + Td) + 1 > Cp || Gr + Tr >= Sp || Gr + Tr > 64 || Gd + Td > 32) {
+        set_last_error("CFAR window too large for a %dx%d map (limits: guard+train <= 64 range, <= 32 Doppler)", Sp, Cp);
+        return MMW_ERR_ARG;
+    }
+    if (cfg->max_det_per_frame < 1 || cfg->max_det_per_frame > 8192) { set_last_error("max_det_per_frame must be 1..8192"); return MMW_ERR_ARG; }
+
+    int dev = cfg->device;
+    if (dev < 0) {
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) { set_last_error("no CUDA device: %s", cudaGetErrorString(e)); return MMW_ERR_CUDA; }
+    }
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        set_last_error("this library is built for sm_100a (B200); device %d is sm_%d%d", dev, prop.major, prop.minor);
+        return MMW_ERR_CUDA;
+    }
+
+    mmw_ctx *c = new mmw_ctx();
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    c->device = dev;
+    c->sm_count = prop.multiProcessorCount;
+    int rc = MMW_OK;
+    auto fail = [&](int code) { mmw_destroy(c); return code; };
+
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { set_last_error("cudaStreamCreate failed"); return fail(MMW_ERR_CUDA); }
+    c->stream = c->own_stream;
+    for (auto &e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { set_last_error("cudaEventCreate failed"); return fail(MMW_ERR_CUDA); }
+
+    const int F = cfg->max_frames;
+    const int n_theta = A <= 64 ? 64 : next_pow2(A);
+    const size_t N = (size_t)Sp * Cp * A, M = (size_t)Sp * Cp;
+
+    if ((rc = dev_alloc(c, &c->d_win_r, (size_t)S))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_win_d, (size_t)C))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_tw_r, (size_t)Sp))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_tw_d, (size_t)Cp))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_tw_a, (size_t)n_theta))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_rs, (size_t)F * A * Sp * C))) return fail(rc);
+    if (cfg->keep_doppler_cube && (rc = dev_alloc(c, &c->d_cube, (size_t)F * N))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_pmap, (size_t)F * M))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_mask, (size_t)F * M / 32))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_dets, (size_t)F * cfg->max_det_per_frame))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_counts, (size_t)F))) return fail(rc);
+    c->dense_cap = F * cfg->max_det_per_frame;
+    if ((rc = dev_alloc(c, &c->d_dense, (size_t)c->dense_cap))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_header, (size_t)4))) return fail(rc);
+    if (cudaMallocHost((void **)&c->h_header, 16) != cudaSuccess ||
+        cudaMallocHost((void **)&c->h_dense, (size_t)c->dense_cap * sizeof(mmw_detection)) != cudaSuccess) {
+        set_last_error("cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(MMW_ERR_CUDA);
+    }
+
+    auto tr = make_twiddles(Sp), td = make_twiddles(Cp), ta = make_twiddles(n_theta);
+    if (cudaMemcpy(c->d_tw_r, tr.data(), Sp * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_tw_d, td.data(), Cp * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_tw_a, ta.data(), n_theta * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("twiddle upload failed");
+        return fail(MMW_ERR_CUDA);
+    }
+
+    PlanDev &p = c->plan;
+    p.S = S; p.C = C; p.A = A; p.Sp = Sp; p.Cp = Cp; p.n_theta = n_theta;
+    p.guard_r = Gr; p.guard_d = Gd; p.win_r_half = Gr + Tr; p.win_d_half = Gd + Td;
+    p.alpha = cfg->cfar_alpha; p.lambda_over_d = cfg->lambda_over_d;
+    p.max_det = cfg->max_det_per_frame; p.keep_cube = cfg->keep_doppler_cube ? 1 : 0; p.frame_offset = 0;
+    p.win_r = c->d_win_r; p.win_d = c->d_win_d; p.tw_r = c->d_tw_r; p.tw_d = c->d_tw_d; p.tw_a = c->d_tw_a;
+
+    if ((rc = mmw_set_windows(c, nullptr, nullptr))) return fail(rc);
+    *out = c;
+    return MMW_OK;
+}
+
+int mmw_get_info(const mmw_ctx *c, mmw_info *info)
+{
+    if (!c || !info) { set_last_error("mmw_get_info: null argument"); return MMW_ERR_ARG; }
+    const PlanDev &p = c->plan;
+    info->Sp = p.Sp; info->Cp = p.Cp; info->n_theta = p.n_theta; info->sm_count = c->sm_count;
+    info->adc_bytes_per_frame = 4LL * p.S * p.C * p.A;
+    const long long N = (long long)p.Sp * p.Cp * p.A, M = (long long)p.Sp * p.Cp;
+    info->algorithmic_bytes_per_frame = 28 * N + 8 * M;
+    info->workspace_bytes = (long long)c->workspace_bytes;
+    info->kernels_per_batch = 5;
+    return MMW_OK;
+}
+
+int mmw_set_windows(mmw_ctx *c, const float *win_range, const float *win_doppler)
+{
+    if (!c) { set_last_error("mmw_set_windows: null context"); return MMW_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    std::vector<float> wr = win_range ? std::vector<float>(win_range, win_range + c->plan.S) : make_hann(c->plan.S);
+    std::vector<float> wd = win_doppler ? std::vector<float>(win_doppler, win_doppler + c->plan.C) : make_hann(c->plan.C);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->d_win_r, wr.data(), wr.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_win_d, wd.data(), wd.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return MMW_OK;
+}
+
+int mmw_get_windows(const mmw_ctx *c, float *win_range, float *win_doppler)
+{
+    if (!c) { set_last_error("mmw_get_windows: null context"); return MMW_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    if (win_range) CK(cudaMemcpy(win_range, c->d_win_r, c->plan.S * sizeof(float), cudaMemcpyDeviceToHost));
+    if (win_doppler) CK(cudaMemcpy(win_doppler, c->d_win_d, c->plan.C * sizeof(float), cudaMemcpyDeviceToHost));
+    return MMW_OK;
+}
+
+int mmw_set_frame_offset(mmw_ctx *c, uint32_t first_frame)
+{
+    if (!c) { set_last_error("mmw_set_frame_offset: null context"); return MMW_ERR_ARG; }
+    c->plan.frame_offset = first_frame;
+    return MMW_OK;
+}
+
+void *mmw_stream(mmw_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int mmw_use_stream(mmw_ctx *c, void *cuda_stream)
+{
+    if (!c) { set_last_error("mmw_use_stream: null context"); return MMW_ERR_ARG; }
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return MMW_OK;
+}
+
+static int run_batch(mmw_ctx *c, const int16_t *adc_dev, int n_frames, cudaEvent_t *stage_ev)
+{
+    const PlanDev &p = c->plan;
+    cudaStream_t st = c->stream;
+    if (stage_ev) CK(cudaEventRecord(stage_ev[0], st));
+    CK(launch_range_fft(p, adc_dev, c->d_rs, n_frames, st));
+    if (stage_ev) CK(cudaEventRecord(stage_ev[1], st));
+    CK(launch_doppler_fft(p, c->d_rs, p.keep_cube ? c->d_cube : nullptr, c->d_pmap, n_frames, st));
+    if (stage_ev) CK(cudaEventRecord(stage_ev[2], st));
+    CK(launch_cfar(p, c->d_pmap, c->d_mask, n_frames, st));
+    if (stage_ev) CK(cudaEventRecord(stage_ev[3], st));
+    CK(launch_detect(p, c->d_rs, c->d_cube, c->d_pmap, c->d_mask, c->d_dets, c->d_counts, n_frames, st));
+    CK(launch_compact(p, c->d_dets, c->d_counts, c->d_dense, c->d_header, n_frames, c->dense_cap, st));
+    if (stage_ev) CK(cudaEventRecord(stage_ev[4], st));
+    c->last_frames = n_frames;
+    return MMW_OK;
+}
+
+static int check_batch_args(mmw_ctx *c, const void *adc, int n_frames, const char *who)
+{
+    if (!c || !adc) { set_last_error("%s: null argument", who); return MMW_ERR_ARG; }
+    if (n_frames < 1 || n_frames > c->cfg.max_frames) {
+        set_last_error("%s: n_frames %d outside 1..max_frames(%d)", who, n_frames, c->cfg.max_frames);
+        return MMW_ERR_ARG;
+    }
+    return MMW_OK;
+}
+
+int mmw_process_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
+{
+    int rc = check_batch_args(c, adc_dev, n_frames, "mmw_process_device");
+    if (rc) return rc;
+    if (((uintptr_t)adc_dev & 15u) != 0) { set_last_error("mmw_process_device: adc_dev must be 16-byte aligned"); return MMW_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    return run_batch(c, adc_dev, n_frames, nullptr);
+}
+
+static int fetch_results(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(c->h_header, c->d_header, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_written = c->h_header[0];
+    uint32_t n = n_written;
+    int rc = c->h_header[3] ? MMW_ERR_OVERFLOW : MMW_OK;
+    if ((int)n > det_capacity) { n = det_capacity > 0 ? (uint32_t)det_capacity : 0; rc = MMW_ERR_OVERFLOW; }
+    if (n > 0) {
+        if (!dets) { set_last_error("detections pointer is null"); return MMW_ERR_ARG; }
+        CK(cudaMemcpyAsync(c->h_dense, c->d_dense, (size_t)n * sizeof(mmw_detection), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(dets, c->h_dense, (size_t)n * sizeof(mmw_detection));
+    }
+    if (n_det) *n_det = (int)n;
+    if (rc == MMW_ERR_OVERFLOW)
+        set_last_error("detection list truncated: %u of %u detections kept", n, c->h_header[1]);
+    return rc;
+}
+
+int mmw_process_host(mmw_ctx *c, const int16_t *adc_host, int n_frames, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    int rc = check_batch_args(c, adc_host, n_frames, "mmw_process_host");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n_frames * 4 * c->plan.S * c->plan.C * c->plan.A;
+    if (!c->d_adc) {            // staging for host captures, allocated on first use
+        rc = dev_alloc(c, &c->d_adc, (size_t)c->cfg.max_frames * 2 * c->plan.S * c->plan.C * c->plan.A);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(c->d_adc, adc_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    rc = run_batch(c, c->d_adc, n_frames, nullptr);
+    if (rc) return rc;
+    return fetch_results(c, dets, det_capacity, n_det);
+}
+
+int mmw_read_detections(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    if (!c) { set_last_error("mmw_read_detections: null context"); return MMW_ERR_ARG; }
+    if (c->last_frames <= 0) { set_last_error("mmw_read_detections: no batch processed"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    return fetch_results(c, dets, det_capacity, n_det);
+}
+
+int mmw_read_counts(mmw_ctx *c, uint32_t *counts, int n_frames)
+{
+    if (!c || !counts) { set_last_error("mmw_read_counts: null argument"); return MMW_ERR_ARG; }
+    if (n_frames < 1 || n_frames > c->last_frames) { set_last_error("mmw_read_counts: n_frames outside the last batch"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(counts, c->d_counts, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MMW_OK;
+}
+
+int mmw_device_results(mmw_ctx *c, const mmw_detection **dense_dets, const uint32_t **header)
+{
+    if (!c) { set_last_error("mmw_device_results: null context"); return MMW_ERR_ARG; }
+    if (dense_dets) *dense_dets = c->d_dense;
+    if (header) *header = c->d_header;
+    return MMW_OK;
+}
+
+static int ensure_scratch(mmw_ctx *c, size_t bytes)
+{
+    if (bytes <= c->scratch_bytes) return MMW_OK;
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_bytes = 0;
+    CK(cudaMalloc(&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    return MMW_OK;
+}
+
+static int check_frame(mmw_ctx *c, int frame, const void *out, const char *who)
+{
+    if (!c || !out) { set_last_error("%s: null argument", who); return MMW_ERR_ARG; }
+    if (frame < 0 || frame >= c->last_frames) { set_last_error("%s: frame %d not in the last batch (%d frames)", who, frame, c->last_frames); return MMW_ERR_STATE; }
+    return MMW_OK;
+}
+
+int mmw_copy_range_spectrum(mmw_ctx *c, int frame, float *out)
+{
+    int rc = check_frame(c, frame, out, "mmw_copy_range_spectrum");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const PlanDev &p = c->plan;
+    const size_t n = (size_t)p.A * p.Sp * p.C;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->d_rs + (size_t)frame * n, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    return MMW_OK;
+}
+
+int mmw_copy_doppler_cube(mmw_ctx *c, int frame, float *out)
+{
+    int rc = check_frame(c, frame, out, "mmw_copy_doppler_cube");
+    if (rc) return rc;
+    if (!c->plan.keep_cube) { set_last_error("mmw_copy_doppler_cube: context was created with keep_doppler_cube = 0"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const PlanDev &p = c->plan;
+    const size_t n = (size_t)p.A * p.Sp * p.Cp;
+    if ((rc = ensure_scratch(c, n * sizeof(float2)))) return rc;
+    CK(launch_export_cube(p, c->d_cube + (size_t)frame * n, (float2 *)c->d_scratch, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->d_scratch, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    return MMW_OK;
+}
+
+int mmw_copy_power_map(mmw_ctx *c, int frame, float *out)
+{
+    int rc = check_frame(c, frame, out, "mmw_copy_power_map");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const PlanDev &p = c->plan;
+    const size_t n = (size_t)p.Sp * p.Cp;
+    if ((rc = ensure_scratch(c, n * sizeof(float)))) return rc;
+    CK(launch_export_pmap(p, c->d_pmap + (size_t)frame * n, (float *)c->d_scratch, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->d_scratch, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return MMW_OK;
+}
+
+int mmw_copy_cfar_mask(mmw_ctx *c, int frame, uint8_t *out)
+{
+    int rc = check_frame(c, frame, out, "mmw_copy_cfar_mask");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const PlanDev &p = c->plan;
+    const size_t n = (size_t)p.Sp * p.Cp;
+    if ((rc = ensure_scratch(c, n))) return rc;
+    CK(launch_export_mask(p, c->d_mask + (size_t)frame * (n / 32), (uint8_t *)c->d_scratch, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->d_scratch, n, cudaMemcpyDeviceToHost));
+    return MMW_OK;
+}
+
+int mmw_time_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames, int iters, float *total_ms, float *per_stage_ms)
+{
+    int rc = check_batch_args(c, adc_dev, n_frames, "mmw_time_device");
+    if (rc) return rc;
+    if (iters < 1 || !total_ms) { set_last_error("mmw_time_device: bad iters / null output"); return MMW_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (per_stage_ms) {
+        // separate instrumented pass: events between launches serialise the stages
+        float acc[4] = {0, 0, 0, 0};
+        for (int i = 0; i < iters; ++i) {
+            rc = run_batch(c, adc_dev, n_frames, c->ev);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(st));
+            for (int s = 0; s < 4; ++s) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, c->ev[s], c->ev[s + 1]));
+                acc[s] += ms;
+            }
+        }
+        for (int s = 0; s < 4; ++s) per_stage_ms[s] = acc[s];
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(c->ev[0], st));
+    for (int i = 0; i < iters; ++i) {
+        rc = run_batch(c, adc_dev, n_frames, nullptr);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(c->ev[5], st));
+    CK(cudaEventSynchronize(c->ev[5]));
+    CK(cudaEventElapsedTime(total_ms, c->ev[0], c->ev[5]));
+    return MMW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// mmw_common.cuh — shared declarations of the B200 radar pipeline (device side).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mmw_radar.h"
+
+namespace mmw {
+
+// ---------------------------------------------------------------------------
+// device-side view of one plan (all pointers are device pointers)
+// ---------------------------------------------------------------------------
+struct PlanDev {
+    int S, C, A;            // samples / chirps / antennas as captured
+    int Sp, Cp;             // FFT lengths (nextPow2)
+    int n_theta;            // angle FFT length
+    int guard_r, guard_d, win_r_half, win_d_half;   // CFAR: guard and guard+train half widths
+    float alpha;
+    float lambda_over_d;
+    int max_det;            // per-frame detection capacity
+    int keep_cube;          // materialise the Doppler cube
+    uint32_t frame_offset;  // added to mmw_detection.frame
+    const float *win_r;     // [S]   range window
+    const float *win_d;     // [C]   Doppler window
+    const float2 *tw_r;     // [Sp]  exp(-2 pi i k / Sp)
+    const float2 *tw_d;     // [Cp]
+    const float2 *tw_a;     // [n_theta]
+};
+
+// internal HBM layouts
+//   adc   [F][C][A][S]  int16 IIQQ   (the reference's capture format)
+//   rs    [F][A][Sp][C] float2       range spectrum, already multiplied by win_d[c]
+//   cube  [F][A][Cp][Sp] float2      Doppler cube (only if keep_cube)
+//   pmap  [F][Cp][Sp]   float        integrated power, range fastest
+//   mask  [F][Cp/32][Sp] uint32      CFAR hits, bit j of word (w, r) <-> doppler 32 w + j
+//   dets  [F][max_det]  mmw_detection, counts [F]
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk tensor-memory-accelerator copies (UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy; completion is signalled on `bar` as transaction bytes.
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_global_f2(float2 *p, float2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers (mmw_pipeline.cu) — return cudaError_t
+// ---------------------------------------------------------------------------
+cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st);
+cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st);
+cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, int n_frames, cudaStream_t st);
+cudaError_t launch_detect(const PlanDev &p, const float2 *rs, const float2 *cube, const float *pmap, const uint32_t *mask,
+                          mmw_detection *dets, uint32_t *counts, int n_frames, cudaStream_t st);
+cudaError_t launch_compact(const PlanDev &p, const mmw_detection *dets, const uint32_t *counts, mmw_detection *dense,
+                           uint32_t *header, int n_frames, int dense_cap, cudaStream_t st);
+// export helpers (not on the hot path): internal layout -> the canonical layouts of mmw_radar.h
+cudaError_t launch_export_cube(const PlanDev &p, const float2 *cube_frame, float2 *out, cudaStream_t st);
+cudaError_t launch_export_pmap(const PlanDev &p, const float *pmap_frame, float *out, cudaStream_t st);
+cudaError_t launch_export_mask(const PlanDev &p, const uint32_t *mask_frame, uint8_t *out, cudaStream_t st);
+bool plan_supported(int Sp, int Cp, const char **why);
+
+// legacy single-frame path (mmw_legacy.cu)
+struct LegacyDev {
+    const float2 *tw;       // [16384]
+    const double2 *base;    // [12800] base frame rx0 (as handed in by the caller)
+    float2 *spectrum;       // [16384] optional export
+    unsigned long long *best;  // packed (|X|^2 bits, ~index)
+};
+
+}  // namespace mmw

@@ -1,0 +1,438 @@
+// mmw_legacy.cu — drop-in for the reference's cudaProcessing() (acceleration.cu:417-572).
+//
+// The reference runs, per 200 KB frame, 6 cudaMalloc + 6 cudaFree + 5 cudaMemcpy + 4 device syncs
+// + 19 launches (unpack, reshape, extension, bit reversal, 14 global-memory radix-2 stages) and then
+// copies the whole fp64 spectrum back to search it on the host.  Here one frame is ONE launch of
+// ONE kernel: rx0 gather + int16 unpack + base-frame subtraction + zero pad + a 16 384-point FFT held
+// entirely in one SM's shared memory (16 x 32 x 32 register butterflies) + the arg-max, with 4 bytes
+// going back to the host.  Device state is created once and reused.
+//
+// Numerics: the FFT runs in fp32 (inputs are int16 differences, exactly representable).  So that the
+// returned distance is the reference's even when two bins are within fp32 rounding of each other,
+// every bin within 1e-4 (relative, power) of the fp32 maximum is re-evaluated in fp64 with a direct
+// DFT and the reference's rule (strict >, ascending bin => first maximum wins, cudaBenchMarking.cpp:
+// 191-206) is applied to the fp64 values.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <mutex>
+
+#include "../../include/mmw_legacy.h"
+#include "../../include/mmw_radar.h"
+#include "fft_regs.cuh"
+
+namespace mmw {
+void set_last_error(const char *fmt, ...);
+}
+
+namespace {
+
+using namespace mmw;
+
+constexpr int kS = 100, kC = 128, kA = 4;          // acceleration.cu:8-11
+constexpr int kValid = kS * kC;                    // 12 800
+constexpr int kN = 16384;                          // nextPow2(12 800), acceleration.cu:465
+constexpr int kSearch = 6553;                      // floor(0.4 * 16384), acceleration.cu:522
+constexpr int kFrameShorts = kS * kC * kA * 2;     // 102 400
+constexpr int kNT = 512;
+constexpr int kMaxCand = 32;
+
+__device__ __forceinline__ int phys(int i) { return i + (i >> 5); }   // one pad slot per 32: conflict-free in all three passes
+
+struct LegacyArgs {
+    const int16_t *frames;      // [n][kFrameShorts]
+    const double2 *base;        // [kValid]
+    const float2 *tw;           // [kN] exp(-2 pi i k / kN)
+    float2 *spectrum;           // [kN] of the LAST frame of the launch, or nullptr
+    int *raw;                   // [n]
+    int size;                   // valid shorts per frame
+};
+
+__device__ __forceinline__ void load_sample(const LegacyArgs &a, const int16_t *frame, int n, double &re, double &im)
+{
+    // rx0 of chirp c, sample s sits at element c*(kA*kS) + s of the [chirp][rx][sample] stream (acceleration.cu:117-150)
+    const int c = n / kS, s = n - c * kS;
+    const int e = c * (kA * kS) + s;
+    const int g = 4 * (e >> 1) + (e & 1);
+    double i16 = 0, q16 = 0;
+    if (g + 2 < a.size) {
+        i16 = (double)frame[g];
+        q16 = (double)frame[g + 2];
+    }
+    const double2 b = a.base[n];
+    re = i16 - b.x;
+    im = q16 - b.y;
+}
+
+__global__ void __launch_bounds__(kNT, 1) legacy_frame_kernel(LegacyArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);                     // [kN + kN/32]
+    __shared__ unsigned long long red_key[kNT / 32];
+    __shared__ double red_d[2][kNT / 32];
+    __shared__ int cand[kMaxCand];
+    __shared__ int n_cand;
+    __shared__ unsigned long long best_key_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int16_t *frame = a.frames + (size_t)blockIdx.x * kFrameShorts;
+    const bool last = blockIdx.x == gridDim.x - 1;
+
+    // ---- gather rx0, subtract the base frame, zero-pad (acceleration.cu:152-166 with the CPU path's padding) ----
+    for (int n = tid; n < kN; n += kNT) {
+        float2 v = make_float2(0.f, 0.f);
+        if (n < kValid) {
+            double re, im;
+            load_sample(a, frame, n, re, im);
+            v = make_float2((float)re, (float)im);
+        }
+        sm[phys(n)] = v;
+    }
+    if (tid == 0) n_cand = 0;
+    __syncthreads();
+
+    // ---- pass 1: 1024 radix-16 butterflies, stride 1024 ----
+#pragma unroll 1
+    for (int j = tid; j < 1024; j += kNT) {
+        float2 x[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[m] = sm[phys(j + 1024 * m)];
+        dft_regs<16>(x);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            float2 v = x[bitrev(q, 4)];
+            if (q > 0) v = cmul(v, a.tw[j * q]);
+            sm[phys(j + 1024 * q)] = v;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: 16 blocks x 32 radix-32 butterflies, stride 32 ----
+    {
+        const int blk = tid >> 5, j = tid & 31;
+        float2 x[32];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) x[m] = sm[phys(blk * 1024 + j + 32 * m)];
+        dft_regs<32>(x);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            float2 v = x[bitrev(q, 5)];
+            if (q > 0) v = cmul(v, a.tw[16 * j * q]);
+            sm[phys(blk * 1024 + j + 32 * q)] = v;
+        }
+    }
+    __syncthreads();
+    // ---- pass 3: 512 radix-32 butterflies on contiguous runs; bin k = q1 + 16 q2 + 512 q3 ----
+    float mag[13];
+    unsigned long long key = 0;
+    {
+        const int q1 = tid >> 5, q2 = tid & 31;
+        float2 x[32];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) x[m] = sm[tid * 33 + m];
+        dft_regs<32>(x);
+#pragma unroll
+        for (int q3 = 0; q3 < 32; ++q3) {
+            const float2 v = x[bitrev(q3, 5)];
+            const int k = q1 + 16 * q2 + 512 * q3;
+            if (a.spectrum != nullptr && last) a.spectrum[k] = v;
+            if (q3 < 13) {
+                const float m2 = v.x * v.x + v.y * v.y;
+                mag[q3] = m2;
+                if (k < kSearch) {
+                    const unsigned long long kk = ((unsigned long long)__float_as_uint(m2) << 32) | (unsigned)(0xffffffffu - (unsigned)k);
+                    key = kk > key ? kk : key;
+                }
+            }
+        }
+    }
+    // block arg-max: larger power wins, equal power -> smaller bin (first maximum, strict >)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if (lane == 0) red_key[warp] = key;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = 0;
+        for (int w = 0; w < kNT / 32; ++w) b = red_key[w] > b ? red_key[w] : b;
+        best_key_s = b;
+    }
+    __syncthreads();
+    const float best_m = __uint_as_float((unsigned)(best_key_s >> 32));
+    int best_k = (int)(0xffffffffu - (unsigned)(best_key_s & 0xffffffffu));
+    if (best_key_s == 0ull) best_k = 0;
+
+    // ---- near ties: collect every bin within 1e-4 of the fp32 maximum ----
+    {
+        const int q1 = tid >> 5, q2 = tid & 31;
+        const float thr = best_m * (1.0f - 1e-4f);
+#pragma unroll
+        for (int q3 = 0; q3 < 13; ++q3) {
+            const int k = q1 + 16 * q2 + 512 * q3;
+            if (k < kSearch && best_m > 0.f && mag[q3] >= thr) {
+                const int slot = atomicAdd(&n_cand, 1);
+                if (slot < kMaxCand) cand[slot] = k;
+            }
+        }
+    }
+    __syncthreads();
+    const int nc = n_cand;
+    if (nc > 1 && nc <= kMaxCand) {
+        if (tid == 0) {                                   // ascending bin order
+            for (int i = 1; i < nc; ++i) {
+                const int v = cand[i];
+                int j = i - 1;
+                while (j >= 0 && cand[j] > v) { cand[j + 1] = cand[j]; --j; }
+                cand[j + 1] = v;
+            }
+        }
+        __syncthreads();
+        double best64 = 0.0;
+        int best64_k = 0;
+        for (int ci = 0; ci < nc; ++ci) {
+            const int k = cand[ci];
+            double sr = 0.0, si = 0.0;
+            for (int n = tid; n < kValid; n += kNT) {
+                double xr, xi, s, c;
+                load_sample(a, frame, n, xr, xi);
+                sincospi((double)((k * n) & (kN - 1)) / (double)(kN / 2), &s, &c);
+                sr += xr * c + xi * s;                     // (xr + j xi)(c - j s)
+                si += xi * c - xr * s;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                si += __shfl_xor_sync(0xffffffffu, si, o);
+            }
+            if (lane == 0) { red_d[0][warp] = sr; red_d[1][warp] = si; }
+            __syncthreads();
+            if (tid == 0) {
+                double r = 0, i = 0;
+                for (int w = 0; w < kNT / 32; ++w) { r += red_d[0][w]; i += red_d[1][w]; }
+                const double m = r * r + i * i;
+                if (m > best64) { best64 = m; best64_k = k; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) a.raw[blockIdx.x] = best64_k;
+    } else if (tid == 0) {
+        a.raw[blockIdx.x] = best_k;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host state (lazy singleton; the reference API has no init/teardown call)
+// ---------------------------------------------------------------------------
+struct LegacyState {
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    int16_t *d_frames = nullptr;
+    int frames_cap = 0;
+    double2 *d_base = nullptr;
+    float2 *d_tw = nullptr;
+    float2 *d_spec = nullptr;
+    int *d_raw = nullptr;
+    int *h_raw = nullptr;          // pinned
+    int raw_cap = 0;
+    double *h_base_copy = nullptr; // last base frame uploaded
+    bool base_valid = false;
+    bool quiet = false;
+};
+LegacyState g;
+std::mutex g_mu;
+
+constexpr int kSmemBytes = (kN + kN / 32) * 8;
+
+#define LCHECK(call)                                                                                      \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            mmw::set_last_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return e_;                                                                                    \
+        }                                                                                                 \
+    } while (0)
+
+cudaError_t ensure_frames(int n)
+{
+    if (n <= g.frames_cap) return cudaSuccess;
+    if (g.d_frames) cudaFree(g.d_frames);
+    if (g.d_raw) cudaFree(g.d_raw);
+    if (g.h_raw) cudaFreeHost(g.h_raw);
+    g.d_frames = nullptr; g.d_raw = nullptr; g.h_raw = nullptr; g.frames_cap = 0;
+    LCHECK(cudaMalloc(&g.d_frames, (size_t)n * kFrameShorts * sizeof(int16_t)));
+    LCHECK(cudaMalloc(&g.d_raw, (size_t)n * sizeof(int)));
+    LCHECK(cudaMallocHost(&g.h_raw, (size_t)n * sizeof(int)));
+    g.frames_cap = n;
+    return cudaSuccess;
+}
+
+cudaError_t ensure_init()
+{
+    if (g.ready) return cudaSuccess;
+    const char *q = getenv("MMW_LEGACY_QUIET");
+    g.quiet = q && q[0] && q[0] != '0';
+    LCHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    LCHECK(cudaMalloc(&g.d_base, kValid * sizeof(double2)));
+    LCHECK(cudaMalloc(&g.d_tw, kN * sizeof(float2)));
+    LCHECK(cudaMalloc(&g.d_spec, kN * sizeof(float2)));
+    float2 *tw = (float2 *)malloc(kN * sizeof(float2));
+    for (int k = 0; k < kN; ++k) {
+        const double th = -2.0 * M_PI * (double)k / (double)kN;
+        tw[k] = make_float2((float)cos(th), (float)sin(th));
+    }
+    cudaError_t e = cudaMemcpy(g.d_tw, tw, kN * sizeof(float2), cudaMemcpyHostToDevice);
+    free(tw);
+    LCHECK(e);
+    g.h_base_copy = (double *)malloc(kValid * 2 * sizeof(double));
+    LCHECK(cudaFuncSetAttribute(legacy_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    LCHECK(ensure_frames(1));
+    g.ready = true;
+    atexit(mmw_legacy_shutdown);
+    return cudaSuccess;
+}
+
+cudaError_t upload_base(const double *base)
+{
+    if (g.base_valid && memcmp(g.h_base_copy, base, kValid * 2 * sizeof(double)) == 0) return cudaSuccess;
+    memcpy(g.h_base_copy, base, kValid * 2 * sizeof(double));
+    LCHECK(cudaMemcpyAsync(g.d_base, g.h_base_copy, kValid * sizeof(double2), cudaMemcpyHostToDevice, g.stream));
+    g.base_valid = true;
+    return cudaSuccess;
+}
+
+// distance formula, operation for operation as acceleration.cu:521-523 / cudaBenchMarking.cpp:301-303
+double distance_from_raw(int raw)
+{
+    const double fs = 2.0e6, lightSpeed = 3.0e08, mu = 5.987e12;
+    const int extendedSize = kN;
+    double Fs_extend = fs * extendedSize / (kC * kS);
+    int maxDisIdx = raw * (kC * kS) / extendedSize;
+    return lightSpeed * (((double)maxDisIdx / extendedSize) * Fs_extend) / (2 * mu);
+}
+
+cudaError_t run_frames(const short *frames, int n, const double *base, int size, bool want_spec)
+{
+    LCHECK(ensure_init());
+    LCHECK(ensure_frames(n));
+    LCHECK(upload_base(base));
+    const int per = size < kFrameShorts ? size : kFrameShorts;
+    if (per == kFrameShorts) {
+        LCHECK(cudaMemcpyAsync(g.d_frames, frames, (size_t)n * kFrameShorts * sizeof(int16_t), cudaMemcpyHostToDevice, g.stream));
+    } else {
+        for (int f = 0; f < n; ++f)
+            LCHECK(cudaMemcpyAsync(g.d_frames + (size_t)f * kFrameShorts, frames + (size_t)f * size, (size_t)per * sizeof(int16_t),
+                                   cudaMemcpyHostToDevice, g.stream));
+    }
+    LegacyArgs a;
+    a.frames = g.d_frames;
+    a.base = g.d_base;
+    a.tw = g.d_tw;
+    a.spectrum = want_spec ? g.d_spec : nullptr;
+    a.raw = g.d_raw;
+    a.size = per;
+    legacy_frame_kernel<<<n, kNT, kSmemBytes, g.stream>>>(a);
+    LCHECK(cudaGetLastError());
+    LCHECK(cudaMemcpyAsync(g.h_raw, g.d_raw, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    LCHECK(cudaStreamSynchronize(g.stream));
+    return cudaSuccess;
+}
+
+double now_s()
+{
+    using clk = std::chrono::steady_clock;
+    return std::chrono::duration<double>(clk::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------- C++-linkage drop-in
+double cudaProcessing(short *input_host, Complex_t *host_baseFrame, int size, double *fftTime, double *preProcessTime,
+                      double *findMaxTime, double *totalTime)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    const double t0 = now_s();
+    cudaError_t e = ensure_init();
+    if (e == cudaSuccess) e = ensure_frames(1);
+    if (e == cudaSuccess) e = upload_base(reinterpret_cast<const double *>(host_baseFrame));
+    const double t1 = now_s();
+    if (e == cudaSuccess) e = run_frames(input_host, 1, reinterpret_cast<const double *>(host_baseFrame), size, true);
+    if (e != cudaSuccess) {
+        // the reference exits silently with the CUDA error code (acceleration.cu:19-31); keep the exit, add the message
+        fprintf(stderr, "cudaProcessing: %s\n", mmw_last_error());
+        exit((int)e);
+    }
+    const double t2 = now_s();
+    const double maxDis = distance_from_raw(g.h_raw[0]);
+    const double t3 = now_s();
+    if (!g.quiet)
+        printf("Inner CUDA Timing:single round processing Time %.5f ms, FFT + findMax %.5f ms Reshape %.5f ms Extension %.5f ms\n",
+               1000.0 * (t3 - t0), 1000.0 * (t3 - t1), 1000.0 * (t1 - t0), 0.0);
+    // the reference accumulates seconds with += (acceleration.cu:534-537)
+    if (totalTime) *totalTime += t3 - t0;
+    if (findMaxTime) *findMaxTime += t3 - t2;
+    if (preProcessTime) *preProcessTime += t1 - t0;     // state check + base-frame upload: everything before the fused launch
+    if (fftTime) *fftTime += t3 - t1;                   // H2D + fused kernel (unpack .. FFT .. arg-max) + 4-byte D2H + formula
+    return maxDis;
+}
+
+// --------------------------------------------------------------------------- C ABI
+extern "C" {
+
+double mmw_legacy_process_frame(const short *frame_host, const double *base_frame_host, int size, int *raw_index)
+{
+    if (!frame_host || !base_frame_host || size <= 0) {
+        mmw::set_last_error("mmw_legacy_process_frame: bad argument");
+        return (double)MMW_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (run_frames(frame_host, 1, base_frame_host, size, true) != cudaSuccess) return (double)MMW_ERR_CUDA;
+    if (raw_index) *raw_index = g.h_raw[0];
+    return distance_from_raw(g.h_raw[0]);
+}
+
+int mmw_legacy_process_frames(const short *frames_host, int n_frames, const double *base_frame_host, int size, double *distances,
+                              int *raw_indices)
+{
+    if (!frames_host || !base_frame_host || n_frames <= 0 || size <= 0 || !distances) {
+        mmw::set_last_error("mmw_legacy_process_frames: bad argument");
+        return MMW_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (run_frames(frames_host, n_frames, base_frame_host, size, true) != cudaSuccess) return MMW_ERR_CUDA;
+    for (int f = 0; f < n_frames; ++f) {
+        distances[f] = distance_from_raw(g.h_raw[f]);
+        if (raw_indices) raw_indices[f] = g.h_raw[f];
+    }
+    return MMW_OK;
+}
+
+int mmw_legacy_copy_spectrum(float *out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.ready || !out) {
+        mmw::set_last_error("mmw_legacy_copy_spectrum: no frame processed yet");
+        return MMW_ERR_STATE;
+    }
+    if (cudaMemcpy(out, g.d_spec, kN * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) return MMW_ERR_CUDA;
+    return MMW_OK;
+}
+
+void mmw_legacy_shutdown(void)
+{
+    if (!g.ready) return;
+    g.ready = false;
+    // at process exit the context may already be gone; ignore errors
+    cudaFree(g.d_frames); cudaFree(g.d_base); cudaFree(g.d_tw); cudaFree(g.d_spec); cudaFree(g.d_raw);
+    cudaFreeHost(g.h_raw);
+    if (g.stream) cudaStreamDestroy(g.stream);
+    free(g.h_base_copy);
+    g = LegacyState();
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+/*
+ * mmw_radar.h — C ABI of the B200-native mmWave radar processing chain.
+ *
+ * This is the NEW surface (plain pointers and sizes, no C++/torch types) for
+ * everything the reference's single entry point cannot carry: batches of
+ * frames, run-time cube dimensions, detection lists, power maps and multi-GPU
+ * frame sharding.  The reference's own entry point
+ *     double cudaProcessing(short*, Complex_t*, int, double*, double*, double*, double*)
+ * (acceleration.h:32, C++ linkage) is kept as a drop-in in mmw_legacy.h.
+ *
+ * What each call replaces in the reference:
+ *   mmw_create / mmw_destroy      the per-frame cudaMalloc x6 / cudaFree x6 of cudaProcessing
+ *                                 (acceleration.cu:435-437,471,474,499 / :564-569): allocated once.
+ *   mmw_process_host              the body of cudaProcessing (acceleration.cu:417-572): H2D of the
+ *                                 int16 capture (:438), unpack (:446), reshape (:454), FFT (:503-510),
+ *                                 peak search (:518-523) — here a batch of frames and the full
+ *                                 range / Doppler / CFAR / angle chain instead of one flat FFT.
+ *   mmw_process_device            same, for captures already resident in HBM.
+ *   mmw_read_* / mmw_copy_*       the reference's D2H of the spectrum (acceleration.cu:519).
+ *   mmw_legacy_*                  see mmw_legacy.h.
+ *
+ * Frame format (identical to the reference capture files, cudaBenchMarking.cpp:156-180):
+ * little-endian int16, per frame [chirp][antenna][sample], samples in groups of four shorts
+ * [I(2m) I(2m+1) Q(2m) Q(2m+1)]; frames concatenated without header.
+ *
+ * All functions return MMW_OK (0) or a negative error code; mmw_last_error() gives the text
+ * of the calling thread's last failure.  There is no CPU fallback: without a CUDA device every
+ * processing call fails with MMW_ERR_CUDA.
+ */
+#ifndef MMW_RADAR_H
+#define MMW_RADAR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMW_OK 0
+#define MMW_ERR_ARG (-1)          /* bad argument / unsupported shape */
+#define MMW_ERR_CUDA (-2)         /* CUDA runtime failure (text in mmw_last_error) */
+#define MMW_ERR_STATE (-3)        /* call not valid in this state (e.g. cube not kept) */
+#define MMW_ERR_OVERFLOW (-4)     /* more detections than the destination can hold (list truncated) */
+
+#define MMW_FLAG_PEAK 0x1u        /* detection is the strict 3x3 maximum among detected cells */
+
+typedef struct mmw_ctx mmw_ctx;
+
+/* 24-byte detection record */
+typedef struct mmw_detection {
+    uint32_t frame;        /* frame index inside the batch (plus frame_offset, see mmw_set_frame_offset) */
+    uint16_t range_bin;    /* 0 .. Sp-1 */
+    uint16_t doppler_bin;  /* 0 .. Cp-1, no fftshift: bins >= Cp/2 are negative velocities */
+    float power;           /* integrated |X|^2 over antennas */
+    float noise;           /* CA-CFAR training mean */
+    int16_t angle_bin;     /* arg-max of the angle FFT wrapped to [-Ntheta/2, Ntheta/2) */
+    uint16_t flags;        /* MMW_FLAG_* */
+    float angle_rad;       /* asin(angle_bin * lambda_over_d / Ntheta) */
+} mmw_detection;
+
+typedef struct mmw_config {
+    int n_samples;          /* S, samples per chirp (multiple of 4; zero-padded to Sp = nextPow2(S), 64..1024) */
+    int n_chirps;           /* C, chirps per frame (multiple of 2; zero-padded to Cp = nextPow2(C), 64..1024) */
+    int n_antennas;         /* A, virtual antennas (1..256) */
+    int max_frames;         /* batch capacity: frames per mmw_process_* call */
+    int cfar_guard_r, cfar_guard_d;   /* guard half-widths (range, Doppler) */
+    int cfar_train_r, cfar_train_d;   /* training half-widths beyond the guard */
+    float cfar_alpha;       /* detect iff P > alpha * mean(training cells) */
+    int max_det_per_frame;  /* capacity of each frame's detection list (<= 8192) */
+    int keep_doppler_cube;  /* 1: write the full Doppler cube to HBM (mmw_copy_doppler_cube works);
+                               0: fused — the angle stage re-derives only the detected cells */
+    float lambda_over_d;    /* wavelength / element spacing, 2.0 for a half-wavelength array */
+    int device;             /* CUDA device ordinal, -1 = current device */
+} mmw_config;
+
+typedef struct mmw_info {
+    int Sp, Cp, n_theta;
+    int sm_count;
+    long long adc_bytes_per_frame;      /* 4*S*C*A */
+    long long algorithmic_bytes_per_frame; /* 28*N + 8*M, SURVEY.md §8d, N = Sp*Cp*A, M = Sp*Cp */
+    long long workspace_bytes;          /* HBM held by the context */
+    int kernels_per_batch;              /* launches one mmw_process_device() issues */
+} mmw_info;
+
+/* defaults: CFAR guard (2,2) train (8,4) alpha 15, 1024 detections/frame, fused cube, lambda/d = 2 */
+void mmw_default_config(mmw_config *cfg, int n_samples, int n_chirps, int n_antennas, int max_frames);
+
+int mmw_create(const mmw_config *cfg, mmw_ctx **out);
+void mmw_destroy(mmw_ctx *ctx);
+const char *mmw_last_error(void);
+int mmw_get_info(const mmw_ctx *ctx, mmw_info *info);
+
+/* Window tables (fp32, host pointers). NULL keeps the default periodic Hann
+ * w[n] = 0.5 - 0.5 cos(2 pi n / L).  win_range has S entries, win_doppler C. */
+int mmw_set_windows(mmw_ctx *ctx, const float *win_range, const float *win_doppler);
+/* copies the tables currently in use back to the host (either pointer may be NULL) */
+int mmw_get_windows(const mmw_ctx *ctx, float *win_range, float *win_doppler);
+/* value added to mmw_detection.frame (the global index of the batch's first frame on this GPU) */
+int mmw_set_frame_offset(mmw_ctx *ctx, uint32_t first_frame);
+
+/* The CUDA stream every call of this context runs on (a cudaStream_t). */
+void *mmw_stream(mmw_ctx *ctx);
+/* Run on a caller-owned stream instead (e.g. torch's current stream); NULL restores the context's own. */
+int mmw_use_stream(mmw_ctx *ctx, void *cuda_stream);
+
+/* ADC cube already in HBM -> detections in HBM. Asynchronous on the context stream.
+ * adc_dev: n_frames * 2*S*C*A int16, 16-byte aligned. */
+int mmw_process_device(mmw_ctx *ctx, const int16_t *adc_dev, int n_frames);
+
+/* Host capture -> detections on the host: H2D, the whole chain, D2H; synchronous.
+ * dets receives up to det_capacity records ordered by (frame, range_bin, doppler_bin);
+ * *n_det is the number written. Returns MMW_ERR_OVERFLOW (after filling dets) if some
+ * frame exceeded max_det_per_frame or the total exceeded det_capacity. */
+int mmw_process_host(mmw_ctx *ctx, const int16_t *adc_host, int n_frames,
+                     mmw_detection *dets, int det_capacity, int *n_det);
+
+/* After mmw_process_device: synchronises, then copies the ordered detection list. */
+int mmw_read_detections(mmw_ctx *ctx, mmw_detection *dets, int det_capacity, int *n_det);
+/* per-frame TRUE detection counts of the last batch (may exceed max_det_per_frame) */
+int mmw_read_counts(mmw_ctx *ctx, uint32_t *counts, int n_frames);
+/* Device views for zero-copy consumers (e.g. an NCCL gather): after mmw_process_device,
+ * *dense_dets points at the packed ordered list and *header at {uint32 n_written, uint32 n_total,
+ * uint32 n_frames, uint32 overflow}. Valid until the next process call. */
+int mmw_device_results(mmw_ctx *ctx, const mmw_detection **dense_dets, const uint32_t **header);
+
+/* Intermediates of one frame of the last batch, copied to the host in canonical layouts
+ * (synchronous, not on the hot path):
+ *   range spectrum [A][Sp][C]  complex64 — NOTE: already multiplied by the Doppler window w_d[c]
+ *   Doppler cube   [A][Sp][Cp] complex64 — needs keep_doppler_cube = 1
+ *   power map      [Sp][Cp]    float32
+ *   CFAR mask      [Sp][Cp]    uint8 */
+int mmw_copy_range_spectrum(mmw_ctx *ctx, int frame, float *out);
+int mmw_copy_doppler_cube(mmw_ctx *ctx, int frame, float *out);
+int mmw_copy_power_map(mmw_ctx *ctx, int frame, float *out);
+int mmw_copy_cfar_mask(mmw_ctx *ctx, int frame, uint8_t *out);
+
+/* Device timing helper: runs mmw_process_device `iters` times back to back on the context
+ * stream between two CUDA events and returns the elapsed milliseconds (total, not per run).
+ * per_stage_ms (optional, 4 floats) receives the summed time of each stage
+ * (range, doppler, cfar, detect+compact) measured with events between the launches. */
+int mmw_time_device(mmw_ctx *ctx, const int16_t *adc_dev, int n_frames, int iters,
+                    float *total_ms, float *per_stage_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

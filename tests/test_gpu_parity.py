@@ -1,0 +1,204 @@
+"""GPU parity: the CUDA chain called through the C ABI against the CPU oracle on the same seeded
+inputs.  Tolerances (BASELINE.json north_star): FFT outputs and power maps within 1e-4 of the
+map's maximum (fp32 vs the fp64 oracle); CFAR hits bit-exact except cells within 1e-5 (relative)
+of their threshold, which are counted and printed; integer/index work bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # relative to the maximum of the array being compared
+NEAR = 1e-5         # |P - thr| <= NEAR * thr  -> cell is "at threshold", excluded from the bit-exact claim
+
+SHAPES = [(64, 64, 2), (100, 128, 4), (128, 64, 12), (256, 128, 4), (512, 256, 12), (1024, 64, 2), (64, 1024, 1), (256, 512, 3)]
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.fixture(scope="module")
+def cases(pkg, orc):
+    """oracle outputs per shape, computed once"""
+    out = {}
+    for (S, C, A) in SHAPES:
+        F = 2 if S * C * A <= 131072 else 1
+        adc = pkg.synth.cube_batch(F, S, C, A, cfg=3, n_targets=5)
+        wr, wd = orc.hann_periodic(S), orc.hann_periodic(C)
+        ref = orc.process_frames(adc, F, S, C, A, wr, wd, want=("rs", "dc", "P", "mask", "noise"), n_threads=4)
+        out[(S, C, A)] = (F, adc, wr, wd, ref)
+    return out
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_range_spectrum(pkg, orc, cases, shape):
+    S, C, A = shape
+    F, adc, wr, wd, ref = cases[shape]
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        ctx.set_windows(None, np.ones(C, np.float32))          # rect Doppler window: plain range FFT
+        ctx.process_host(adc, F)
+        for f in range(F):
+            assert relmax(ctx.range_spectrum(f), ref["rs"][f]) < TOL
+        ctx.set_windows(None, None)                            # default Hann: K1 folds w_d[c] into its output
+        ctx.process_host(adc, F)
+        assert relmax(ctx.range_spectrum(0), ref["rs"][0] * wd.astype(np.float64)) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_doppler_cube_and_power_map(pkg, orc, cases, shape):
+    S, C, A = shape
+    F, adc, wr, wd, ref = cases[shape]
+    with pkg.RadarContext(S, C, A, F, keep_doppler_cube=True) as ctx:
+        ctx.process_host(adc, F)
+        for f in range(F):
+            assert relmax(ctx.doppler_cube(f), ref["dc"][f]) < TOL
+            assert relmax(ctx.power_map(f), ref["P"][f]) < TOL
+    with pkg.RadarContext(S, C, A, F, keep_doppler_cube=False) as ctx:
+        ctx.process_host(adc, F)
+        assert relmax(ctx.power_map(F - 1), ref["P"][F - 1]) < TOL
+        with pytest.raises(pkg.RadarError):
+            ctx.doppler_cube(0)
+
+
+def _near_threshold(ref, alpha):
+    thr = alpha * ref["noise"]
+    return np.abs(ref["P"] - thr) <= NEAR * thr
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("keep", [False, True])
+def test_cfar_and_detections(pkg, orc, cases, shape, keep):
+    S, C, A = shape
+    F, adc, wr, wd, ref = cases[shape]
+    alpha = 15.0
+    near = _near_threshold(ref, alpha)
+    with pkg.RadarContext(S, C, A, F, keep_doppler_cube=keep) as ctx:
+        dets, overflow = ctx.process_host(adc, F)
+        assert not overflow
+        counts = ctx.read_counts(F)
+        for f in range(F):
+            m = ctx.cfar_mask(f)
+            bad = (m != ref["mask"][f]) & ~near[f]
+            assert not bad.any(), f"{bad.sum()} CFAR cells differ away from threshold"
+            assert counts[f] == m.sum()
+    print(f"\n{shape} keep={keep}: {len(dets)} detections, {int(near.sum())} cells within {NEAR} of threshold (excluded)")
+    # ordering and identity of the hit list
+    key = lambda d: (int(d["frame"]), int(d["range_bin"]), int(d["doppler_bin"]))
+    got, want = [key(d) for d in dets], [key(d) for d in ref["dets"]]
+    assert got == sorted(got)
+    diff = set(got) ^ set(want)
+    assert all(near[k] for k in diff)
+    by = {key(d): d for d in ref["dets"]}
+    n_theta = orc.angle_fft_size(A)
+    assert len(dets) > 0
+    for d in dets:
+        k = key(d)
+        if k not in by:
+            continue
+        o = by[k]
+        assert abs(d["power"] - o["power"]) <= TOL * ref["P"][k[0]].max()
+        assert abs(d["noise"] - o["noise"]) <= 1e-3 * o["noise"] + TOL * 1e-3 * ref["P"][k[0]].max()
+        x = ref["dc"][k[0]][:, k[1], k[2]]
+        _, ratio = orc.angle_argmax(x, n_theta)
+        if ratio < 1 - 1e-4:                                   # angle arg-max not a near tie
+            assert d["angle_bin"] == o["angle_bin"]
+            assert abs(d["angle_rad"] - o["angle_rad"]) < 1e-5
+        # grouping flag: compare unless a detected neighbour has (almost) the same power
+        P = ref["P"][k[0]]
+        nb = [P[k[1] + i, (k[2] + j) % P.shape[1]] for i in (-1, 0, 1) for j in (-1, 0, 1)
+              if (i or j) and 0 <= k[1] + i < P.shape[0] and ref["mask"][k[0]][k[1] + i, (k[2] + j) % P.shape[1]]]
+        if all(abs(v - P[k[1], k[2]]) > 1e-4 * P[k[1], k[2]] for v in nb) and not any(near[k[0]][max(0, k[1] - 1):k[1] + 2].ravel()):
+            assert (d["flags"] & 1) == (o["flags"] & 1)
+
+
+def test_detection_list_overflow_is_ordered_and_counted(pkg, orc):
+    S, C, A, F = 64, 64, 2, 3
+    rng = np.random.default_rng(5)
+    adc = rng.integers(-3000, 3000, (F, 2 * S * C * A)).astype(np.int16)
+    with pkg.RadarContext(S, C, A, F, cfar_alpha=1.5, max_det_per_frame=4096) as ctx:
+        full, ov = ctx.process_host(adc, F)
+        counts_full = ctx.read_counts(F)
+        assert not ov and len(full) == counts_full.sum() and counts_full.min() > 16
+    with pkg.RadarContext(S, C, A, F, cfar_alpha=1.5, max_det_per_frame=16) as ctx:
+        cut, ov = ctx.process_host(adc, F)
+        assert ov and np.array_equal(ctx.read_counts(F), counts_full)        # true totals still reported
+        want = np.concatenate([full[full["frame"] == f][:16] for f in range(F)])
+        assert cut.tobytes() == want.tobytes()                              # first 16 per frame, in order
+        few, ov2 = ctx.process_host(adc, F, det_capacity=5)
+        assert ov2 and few.tobytes() == want[:5].tobytes()
+
+
+def test_empty_scene_and_zero_input(pkg):
+    S, C, A, F = 128, 64, 4, 2
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        dets, ov = ctx.process_host(np.zeros((F, 2 * S * C * A), np.int16), F)
+        assert len(dets) == 0 and not ov and ctx.read_counts(F).sum() == 0
+        assert ctx.power_map(1).max() == 0.0
+        with pytest.raises(pkg.RadarError):
+            ctx.process_host(np.zeros((F + 1, 2 * S * C * A), np.int16), F + 1)     # beyond max_frames
+        with pytest.raises(pkg.RadarError):
+            ctx.power_map(F)                                                        # frame outside the batch
+
+
+def test_user_windows_round_trip(pkg, orc):
+    S, C, A = 64, 64, 2
+    adc = pkg.synth.cube_batch(1, S, C, A, cfg=8)
+    wr = np.hamming(S).astype(np.float32)
+    wd = np.blackman(C).astype(np.float32)
+    with pkg.RadarContext(S, C, A, 1, keep_doppler_cube=True) as ctx:
+        ctx.set_windows(wr, wd)
+        g = ctx.get_windows()
+        assert np.array_equal(g[0], wr) and np.array_equal(g[1], wd)
+        ctx.process_host(adc, 1)
+        ref = orc.process_frames(adc, 1, S, C, A, wr, wd, want=("dc", "P"))
+        assert relmax(ctx.doppler_cube(0), ref["dc"][0]) < TOL and relmax(ctx.power_map(0), ref["P"][0]) < TOL
+        # default windows are the oracle's periodic Hann, bit for bit
+        ctx.set_windows(None, None)
+        g = ctx.get_windows()
+        assert np.array_equal(g[0], orc.hann_periodic(S)) and np.array_equal(g[1], orc.hann_periodic(C))
+
+
+# ---------------------------------------------------------------- legacy path (reference cfg 100 x 128 x 4)
+def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir):
+    gold = np.load(f"{golden_dir}/legacy_reference.npz")
+    i = 0
+    timers = np.zeros(4)
+    for sd in gold["cap_seeds"]:
+        cap = pkg.synth.legacy_capture(int(gold["cap_frames"]), seed=int(sd), moving=(sd == 2))
+        base = orc.reshape(cap[0], 100, 128, 4)[:12800]
+        for f in range(1, cap.shape[0]):
+            d = pkg.cudaProcessing(cap[f], base, timers=timers)            # the reference's own symbol
+            assert d == gold["dist"][i], (d, gold["dist"][i])            # bit-identical double
+            spec = pkg.api.legacy_spectrum()
+            probes = gold["spec_probes"][i]
+            assert np.abs(spec[gold["probe_bins"]] - probes).max() <= TOL * np.abs(probes).max()
+            d2, raw = pkg.api.legacy_process_frame(cap[f], base)
+            assert raw == gold["raw"][i] and d2 == d
+            i += 1
+        dist, raw = pkg.api.legacy_process_frames(cap[1:], base)
+        n = cap.shape[0] - 1
+        assert np.array_equal(dist, gold["dist"][i - n:i]) and np.array_equal(raw, gold["raw"][i - n:i])
+    assert timers[3] > 0 and timers[3] >= timers[0] > 0                   # accumulated seconds (+=)
+
+
+def test_legacy_full_spectrum_and_edges(pkg, orc):
+    cap = pkg.synth.legacy_capture(3, seed=21)
+    base = orc.reshape(cap[0], 100, 128, 4)[:12800]
+    d_ref, raw_ref, spec_ref = orc.legacy_frame(cap[2], base, want_spectrum=True)
+    d, raw = pkg.api.legacy_process_frame(cap[2], base)
+    assert (d, raw) == (d_ref, raw_ref)
+    assert relmax(pkg.api.legacy_spectrum(), spec_ref) < TOL
+    # all-zero difference -> arg-max 0 -> 0 m (strict >, cudaBenchMarking.cpp:199)
+    assert pkg.api.legacy_process_frame(cap[0], base) == (0.0, 0)
+    # the caller may change the base frame between calls (the reference re-uploads it every call)
+    base2 = orc.reshape(cap[1], 100, 128, 4)[:12800]
+    assert pkg.api.legacy_process_frame(cap[2], base2) == orc.legacy_frame(cap[2], base2)
+    assert pkg.api.legacy_process_frame(cap[2], base) == (d_ref, raw_ref)
+    # two bins with the same power: the first wins, as in the reference
+    k = np.arange(100)
+    tone = lambda f0: 1000 * np.exp(2j * np.pi * f0 * k)
+    z = np.zeros((128, 4, 100), complex)
+    z[:, 0, :] = tone(0.11) + tone(0.23)
+    frame = pkg.synth.pack_iiqq(z).reshape(-1)
+    zero_base = np.zeros(12800, complex)
+    assert pkg.api.legacy_process_frame(frame, zero_base) == orc.legacy_frame(frame, zero_base)

@@ -1,0 +1,97 @@
+"""Size-independent properties at the full BASELINE.json shapes (the oracle is too slow to check every
+frame there): exact power-of-two scaling, energy conservation, determinism, batch independence and
+sharded == unsharded."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FULL = [(256, 128, 4, 32), (512, 256, 12, 4)]
+
+
+@pytest.fixture(scope="module")
+def batches(pkg):
+    return {(S, C, A): pkg.synth.cube_batch(F, S, C, A, cfg=2 if A == 4 else 3, n_targets=8) for (S, C, A, F) in FULL}
+
+
+@pytest.mark.parametrize("S,C,A,F", FULL)
+def test_power_of_two_scaling_is_exact(pkg, batches, S, C, A, F):
+    adc = batches[(S, C, A)]
+    half = (adc // 2 * 2 // 2).astype(np.int16)                 # any int16 data; doubled stays in range (|x| <= 16384)
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        d1, _ = ctx.process_host(half, F)
+        p1 = ctx.power_map(F - 1)
+        d2, _ = ctx.process_host((half * 2).astype(np.int16), F)
+        p2 = ctx.power_map(F - 1)
+    assert np.array_equal(p2, 4.0 * p1)                         # every fp32 op scales exactly by 2
+    assert np.array_equal(d1["range_bin"], d2["range_bin"]) and np.array_equal(d1["doppler_bin"], d2["doppler_bin"])
+    assert np.array_equal(d2["power"], 4 * d1["power"]) and np.array_equal(d1["angle_bin"], d2["angle_bin"])
+
+
+@pytest.mark.parametrize("S,C,A,F", FULL)
+def test_energy_conservation(pkg, batches, S, C, A, F):
+    adc = batches[(S, C, A)]
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        wr, wd = ctx.get_windows()
+        ctx.process_host(adc, F)
+        for f in (0, F - 1):
+            z = pkg.synth.unpack_iiqq(adc[f].reshape(C, A, 2 * S))
+            e_in = (np.abs(z * wr[None, None, :] * wd[:, None, None]) ** 2).sum()
+            e_out = ctx.power_map(f).astype(np.float64).sum()
+            assert abs(e_out / (ctx.Sp * ctx.Cp) - e_in) <= 1e-5 * e_in       # Parseval, unnormalised 2-D FFT
+
+
+@pytest.mark.parametrize("S,C,A,F", FULL)
+def test_deterministic_and_batch_independent(pkg, batches, S, C, A, F):
+    adc = batches[(S, C, A)]
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        a, _ = ctx.process_host(adc, F)
+        b, _ = ctx.process_host(adc, F)
+        assert a.tobytes() == b.tobytes() and len(a) > 0
+        keys = a["frame"].astype(np.int64) << 32 | a["range_bin"].astype(np.int64) << 16 | a["doppler_bin"]
+        assert np.all(np.diff(keys) > 0)
+        # a frame processed alone gives the records it gets inside the batch
+        ctx.set_frame_offset(F - 1)
+        one, _ = ctx.process_host(adc[F - 1:], 1)
+        assert one.tobytes() == a[a["frame"] == F - 1].tobytes()
+
+
+@pytest.mark.parametrize("S,C,A,F", FULL)
+def test_sharded_equals_unsharded(pkg, batches, S, C, A, F):
+    """two 'ranks' emulated as two contexts on one GPU, each with its own contiguous frame block"""
+    adc = batches[(S, C, A)]
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        whole, _ = ctx.process_host(adc, F)
+    parts = []
+    for rank in range(3):
+        first, cnt = pkg.sharding.shard_frames(F, 3, rank)
+        with pkg.RadarContext(S, C, A, max(cnt, 1)) as ctx:
+            ctx.set_frame_offset(first)
+            if cnt:
+                parts.append(ctx.process_host(adc[first:first + cnt], cnt)[0])
+    assert np.concatenate(parts).tobytes() == whole.tobytes()
+
+
+def test_device_resident_path_and_stream(pkg, batches):
+    import torch
+
+    S, C, A, F = FULL[0]
+    adc = batches[(S, C, A)]
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        host, _ = ctx.process_host(adc, F)
+        dev = torch.from_numpy(adc).cuda()
+        s = torch.cuda.Stream()
+        ctx.use_stream(s.cuda_stream)
+        with torch.cuda.stream(s):
+            ctx.process_device(dev, F)
+        s.synchronize()
+        got, _ = ctx.read_detections()
+        assert got.tobytes() == host.tobytes()
+        dense, header = ctx.device_results()
+        hdr = pkg.sharding.device_bytes_view(header, 16, dev.device).cpu().numpy().view(np.uint32)
+        assert hdr[0] == len(host) and hdr[2] == F and hdr[3] == 0
+        recs = pkg.sharding.records_from_bytes(pkg.sharding.device_bytes_view(dense, 24 * len(host), dev.device), pkg.DET_DTYPE)
+        assert recs.tobytes() == host.tobytes()
+        ctx.use_stream(None)
+        ms = ctx.time_device(dev, F, 2)
+        assert ms > 0
