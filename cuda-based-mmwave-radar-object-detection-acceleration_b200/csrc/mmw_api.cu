@@ -44,15 +44,18 @@ struct mmw_ctx {
     cudaStream_t stream;
     // tables
     float *d_win_r, *d_win_d;
-    float2 *d_tw_r, *d_tw_d, *d_tw_a;
+    float2 *d_tw_d, *d_tw_a, *d_tw1_r, *d_tw1_d;
     // workspace
     int16_t *d_adc;          // staging for host captures
     float2 *d_rs;
     float2 *d_cube;
     float *d_pmap;
     uint32_t *d_mask;
-    mmw_detection *d_dets;
+    float *d_noise;
+    uint32_t *d_keys;
     uint32_t *d_counts;
+    uint32_t *d_offsets;
+    unsigned int *d_ticket;
     mmw_detection *d_dense;
     uint32_t *d_header;
     void *d_scratch;         // export scratch
@@ -94,6 +97,20 @@ static std::vector<float2> make_twiddles(int n)
     return t;
 }
 
+// W_n^(n2*k1) for the two-pass plan of length n, laid out in the order pass 1 reads it (see tw1_index in mmw_pipeline.cu)
+static std::vector<float2> make_pass1_twiddles(int n)
+{
+    int r1 = 0, r2 = 0;
+    plan_radices(n, &r1, &r2);
+    std::vector<float2> t(n);
+    for (int n2 = 0; n2 < r2; ++n2)
+        for (int k1 = 0; k1 < r1; ++k1) {
+            const double th = -2.0 * M_PI * (double)((n2 * k1) % n) / (double)n;
+            t[((n2 >> 1) * r1 + k1) * 2 + (n2 & 1)] = make_float2((float)cos(th), (float)sin(th));
+        }
+    return t;
+}
+
 static std::vector<float> make_hann(int n)
 {
     std::vector<float> w(n);
@@ -128,9 +145,9 @@ void mmw_destroy(mmw_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw_r); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
+    cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
     cudaFree(c->d_adc); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_mask);
-    cudaFree(c->d_dets); cudaFree(c->d_counts); cudaFree(c->d_dense); cudaFree(c->d_header); cudaFree(c->d_scratch);
+    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_dense); cudaFree(c->d_header); cudaFree(c->d_scratch);
     if (c->h_header) cudaFreeHost(c->h_header);
     if (c->h_dense) cudaFreeHost(c->h_dense);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -189,15 +206,20 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
 
     if ((rc = dev_alloc(c, &c->d_win_r, (size_t)S))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_win_d, (size_t)C))) return fail(rc);
-    if ((rc = dev_alloc(c, &c->d_tw_r, (size_t)Sp))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_tw1_r, (size_t)Sp))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_tw1_d, (size_t)Cp))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_tw_d, (size_t)Cp))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_tw_a, (size_t)n_theta))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_rs, (size_t)F * A * Sp * C))) return fail(rc);
     if (cfg->keep_doppler_cube && (rc = dev_alloc(c, &c->d_cube, (size_t)F * N))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_pmap, (size_t)F * M))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_mask, (size_t)F * M / 32))) return fail(rc);
-    if ((rc = dev_alloc(c, &c->d_dets, (size_t)F * cfg->max_det_per_frame))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_noise, (size_t)F * M))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_keys, (size_t)F * cfg->max_det_per_frame))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_counts, (size_t)F))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_offsets, (size_t)F + 1))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_ticket, (size_t)1))) return fail(rc);
+    if (cudaMemset(c->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     c->dense_cap = F * cfg->max_det_per_frame;
     if ((rc = dev_alloc(c, &c->d_dense, (size_t)c->dense_cap))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_header, (size_t)4))) return fail(rc);
@@ -207,8 +229,10 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
         return fail(MMW_ERR_CUDA);
     }
 
-    auto tr = make_twiddles(Sp), td = make_twiddles(Cp), ta = make_twiddles(n_theta);
-    if (cudaMemcpy(c->d_tw_r, tr.data(), Sp * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+    auto td = make_twiddles(Cp), ta = make_twiddles(n_theta);
+    auto t1r = make_pass1_twiddles(Sp), t1d = make_pass1_twiddles(Cp);
+    if (cudaMemcpy(c->d_tw1_r, t1r.data(), Sp * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_tw1_d, t1d.data(), Cp * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(c->d_tw_d, td.data(), Cp * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(c->d_tw_a, ta.data(), n_theta * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_last_error("twiddle upload failed");
@@ -220,7 +244,7 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     p.guard_r = Gr; p.guard_d = Gd; p.win_r_half = Gr + Tr; p.win_d_half = Gd + Td;
     p.alpha = cfg->cfar_alpha; p.lambda_over_d = cfg->lambda_over_d;
     p.max_det = cfg->max_det_per_frame; p.keep_cube = cfg->keep_doppler_cube ? 1 : 0; p.frame_offset = 0;
-    p.win_r = c->d_win_r; p.win_d = c->d_win_d; p.tw_r = c->d_tw_r; p.tw_d = c->d_tw_d; p.tw_a = c->d_tw_a;
+    p.win_r = c->d_win_r; p.win_d = c->d_win_d; p.tw_d = c->d_tw_d; p.tw_a = c->d_tw_a; p.tw1_r = c->d_tw1_r; p.tw1_d = c->d_tw1_d;
 
     if ((rc = mmw_set_windows(c, nullptr, nullptr))) return fail(rc);
     *out = c;
@@ -286,10 +310,13 @@ static int run_batch(mmw_ctx *c, const int16_t *adc_dev, int n_frames, cudaEvent
     if (stage_ev) CK(cudaEventRecord(stage_ev[1], st));
     CK(launch_doppler_fft(p, c->d_rs, p.keep_cube ? c->d_cube : nullptr, c->d_pmap, n_frames, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[2], st));
-    CK(launch_cfar(p, c->d_pmap, c->d_mask, n_frames, st));
+    CK(launch_cfar(p, c->d_pmap, c->d_mask, c->d_noise, n_frames, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[3], st));
-    CK(launch_detect(p, c->d_rs, c->d_cube, c->d_pmap, c->d_mask, c->d_dets, c->d_counts, n_frames, st));
-    CK(launch_compact(p, c->d_dets, c->d_counts, c->d_dense, c->d_header, n_frames, c->dense_cap, st));
+    DetectBuffers b;
+    b.rs = c->d_rs; b.cube = c->d_cube; b.pmap = c->d_pmap; b.noise_map = c->d_noise; b.mask = c->d_mask;
+    b.keys = c->d_keys; b.counts = c->d_counts; b.offsets = c->d_offsets; b.header = c->d_header;
+    b.ticket = c->d_ticket; b.dense = c->d_dense;
+    CK(launch_detect(p, b, n_frames, c->dense_cap, c->sm_count, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[4], st));
     c->last_frames = n_frames;
     return MMW_OK;

@@ -22,8 +22,9 @@ struct PlanDev {
     uint32_t frame_offset;  // added to mmw_detection.frame
     const float *win_r;     // [S]   range window
     const float *win_d;     // [C]   Doppler window
-    const float2 *tw_r;     // [Sp]  exp(-2 pi i k / Sp)
-    const float2 *tw_d;     // [Cp]
+    const float2 *tw_d;     // [Cp]  exp(-2 pi i k / Cp), natural order (fused-mode Doppler bin evaluation)
+    const float2 *tw1_r;    // [Sp]  pass-1 twiddles of the range FFT in consumption order (tw1_index)
+    const float2 *tw1_d;    // [Cp]  pass-1 twiddles of the Doppler FFT in consumption order
     const float2 *tw_a;     // [n_theta]
 };
 
@@ -33,7 +34,8 @@ struct PlanDev {
 //   cube  [F][A][Cp][Sp] float2      Doppler cube (only if keep_cube)
 //   pmap  [F][Cp][Sp]   float        integrated power, range fastest
 //   mask  [F][Cp/32][Sp] uint32      CFAR hits, bit j of word (w, r) <-> doppler 32 w + j
-//   dets  [F][max_det]  mmw_detection, counts [F]
+//   keys  [F][max_det]  uint32 (range<<16 | doppler), counts [F], offsets [F+1]
+//   dense [<= F*max_det] mmw_detection, ordered by (frame, range, doppler); header[4]
 
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk tensor-memory-accelerator copies (UBLKCP)
@@ -90,16 +92,28 @@ __device__ __forceinline__ void st_global_f2(float2 *p, float2 v)
 // ---------------------------------------------------------------------------
 cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st);
 cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st);
-cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, int n_frames, cudaStream_t st);
-cudaError_t launch_detect(const PlanDev &p, const float2 *rs, const float2 *cube, const float *pmap, const uint32_t *mask,
-                          mmw_detection *dets, uint32_t *counts, int n_frames, cudaStream_t st);
-cudaError_t launch_compact(const PlanDev &p, const mmw_detection *dets, const uint32_t *counts, mmw_detection *dense,
-                           uint32_t *header, int n_frames, int dense_cap, cudaStream_t st);
+// everything stages 3/4 read and write (device pointers)
+struct DetectBuffers {
+    const float2 *rs;
+    const float2 *cube;
+    const float *pmap;
+    float *noise_map;       // [F][Cp][Sp], valid at hit cells only
+    uint32_t *mask;         // [F][Cp/32][Sp]
+    uint32_t *keys;         // [F][max_det]  (range << 16 | doppler), ordered
+    uint32_t *counts;       // [F]    true hit count per frame
+    uint32_t *offsets;      // [F+1]  exclusive scan of min(count, max_det)
+    uint32_t *header;       // {n_written, n_total, n_frames, overflow}
+    unsigned int *ticket;   // last-CTA-done counter (self-resetting)
+    mmw_detection *dense;   // ordered detection list of the batch
+};
+cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, cudaStream_t st);
+cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st);
 // export helpers (not on the hot path): internal layout -> the canonical layouts of mmw_radar.h
 cudaError_t launch_export_cube(const PlanDev &p, const float2 *cube_frame, float2 *out, cudaStream_t st);
 cudaError_t launch_export_pmap(const PlanDev &p, const float *pmap_frame, float *out, cudaStream_t st);
 cudaError_t launch_export_mask(const PlanDev &p, const uint32_t *mask_frame, uint8_t *out, cudaStream_t st);
 bool plan_supported(int Sp, int Cp, const char **why);
+void plan_radices(int n, int *r1, int *r2);
 
 // legacy single-frame path (mmw_legacy.cu)
 struct LegacyDev {

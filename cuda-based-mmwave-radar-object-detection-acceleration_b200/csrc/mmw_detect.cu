@@ -1,0 +1,478 @@
+// mmw_detect.cu — stages 3 and 4 of the chain: power map -> detection records.
+//
+//   K3  cfar_kernel     2-D cell-averaging CFAR on the integrated power map.  Range axis clamps
+//                       (training count recounted), Doppler axis wraps.  Emits a bit mask and, for
+//                       hit cells only, the noise estimate.
+//   K4a list_kernel     per frame: ordered compaction of the mask bits into (range, doppler) keys and
+//                       the per-frame count; the last CTA to finish scans the counts into offsets of
+//                       the dense list and writes the header (no extra launch, no host round trip).
+//   K4b measure_kernel  one warp per detection over the whole batch: 3x3 peak grouping, antenna
+//                       snapshot (from the Doppler cube, or re-derived from the range spectrum in fused
+//                       mode), angle spectrum arg-max; records go straight into the dense ordered list.
+//
+// The reference has no counterpart for any of this; its only "detector" is the
+// host arg-max of acceleration.cu:391-407.
+//
+// Numerical note on the CFAR sums.  A target cell is up to ~1e9 x the noise floor after the 2-D FFT
+// gain, so running sums with subtraction, prefix-sum differences and "outer box minus inner box" are
+// all unusable in fp32: they leave an error of tens of noise floors behind every strong cell.  Every
+// sum below therefore only ever ADDS training cells: per row a `full` window sum and a `ring` sum
+// (full minus the guard span, computed as left + right), then a column sum that takes `ring` rows
+// inside the Doppler guard and `full` rows outside it.
+#include "mmw_common.cuh"
+
+namespace mmw {
+
+constexpr int kCfarRT = 64;      // range bins per tile
+constexpr int kCfarDT = 32;      // Doppler bins per tile (one mask word per range bin)
+constexpr int kCfarNT = 256;
+constexpr int kCfarRS = kCfarRT + 4;   // row stride of the row-sum arrays (16-byte aligned rows)
+
+// FIXED = the default geometry (guard 2x2, train 8x4): fully unrolled register-window version.
+// Generic geometries take the run-time-bound version below (same sums, same association per cell).
+//
+// FIXED data flow per 64 x 32 tile (+ halo 10 range / 6 Doppler):
+//   load   tile[44][84]                              coalesced, Doppler wrapped, range zero-filled
+//   rows   a thread makes 8 adjacent range cells of one row from 28 register values: sliding sums by
+//          pairwise doubling (s2 -> s4 -> s8), no subtraction anywhere
+//   cols   a thread makes 4 adjacent Doppler cells of one range bin from 22 register values (lanes run
+//          along range, so every shared-memory access is stride-1)
+//   hits   4 bits per thread OR-ed into the tile's 64 mask words; noise stored for hit cells only
+template <bool FIXED>
+__global__ void __launch_bounds__(kCfarNT) cfar_kernel(PlanDev p, const float *__restrict__ pmap, uint32_t *__restrict__ mask,
+                                                       float *__restrict__ noise_map)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int Gr = FIXED ? 2 : p.guard_r, Gd = FIXED ? 2 : p.guard_d;
+    const int Wr = FIXED ? 10 : p.win_r_half, Wd = FIXED ? 6 : p.win_d_half;
+    const int Sp = p.Sp, Cp = p.Cp;
+    const int Lp = FIXED ? 12 : ((Wr + 3) & ~3);         // halo rounded up to whole float4 chunks
+    const int tw_ = kCfarRT + 2 * Lp;                    // tile width (range, fastest)
+    const int th_ = kCfarDT + 2 * Wd;                    // tile height (Doppler)
+    constexpr int RS = kCfarRS;
+    float *tile = reinterpret_cast<float *>(smem);       // [th_][tw_]
+    float *fullS = tile + th_ * tw_;                     // [th_][RS]
+    float *ringS = fullS + th_ * RS;                     // [th_][RS]
+    uint32_t *words = reinterpret_cast<uint32_t *>(ringS + th_ * RS);   // [RT]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = blockIdx.x * kCfarRT;
+    const int dblk = blockIdx.y;
+    const int f = blockIdx.z;
+    const int d0 = dblk * kCfarDT;
+    const float *pf = pmap + (size_t)f * Cp * Sp;
+
+    // ---- tile + halo, staged with 16-byte cp.async (all copies in flight at once; zero-fill outside
+    //      [0, Sp) -- adding +0 is exact); Doppler wraps.  Tile column 0 is range bin r0 - Lp. ----
+    if (tid < kCfarRT) words[tid] = 0u;
+    {
+        const int qpr = tw_ / 4;                             // float4 chunks per tile row
+        for (int i = tid; i < th_ * qpr; i += kCfarNT) {
+            const int j = i / qpr, x4 = (i - j * qpr) * 4;
+            const int d = (d0 - Wd + j + Cp) & (Cp - 1);
+            const int r = r0 - Lp + x4;
+            const bool in = (r >= 0 && r < Sp);
+            const float *src = pf + (size_t)d * Sp + (in ? r : 0);
+            const uint32_t dst = smem_u32(tile + j * tw_ + x4);
+            const int nbytes = in ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+
+    if constexpr (FIXED) {
+        // ---- row pass: 44 rows x 8 segments of 8 cells ----
+        for (int t = tid; t < 44 * (kCfarRT / 8); t += kCfarNT) {
+            const int j = t >> 3, x0 = (t & 7) * 8;
+            const float4 *c4 = reinterpret_cast<const float4 *>(tile + j * tw_ + x0);   // v[i] = offset (i - 12) of cell x0
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 q = c4[i];
+                v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+            }
+            float s2[31], s4[29], ring[8], full[8];
+#pragma unroll
+            for (int i = 0; i < 31; ++i) s2[i] = v[i] + v[i + 1];
+#pragma unroll
+            for (int i = 0; i < 29; ++i) s4[i] = s2[i] + s2[i + 2];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float left = s4[q + 2] + s4[q + 6];         // v[q+2 .. q+9]    offsets -10 .. -3
+                const float right = s4[q + 15] + s4[q + 19];      // v[q+15 .. q+22]  offsets  +3 .. +10
+                const float mid = s4[q + 10] + v[q + 14];         // v[q+10 .. q+14]  offsets  -2 .. +2
+                ring[q] = left + right;
+                full[q] = ring[q] + mid;
+            }
+            float4 *fo = reinterpret_cast<float4 *>(fullS + j * RS + x0);
+            float4 *ro = reinterpret_cast<float4 *>(ringS + j * RS + x0);
+            fo[0] = make_float4(full[0], full[1], full[2], full[3]);
+            fo[1] = make_float4(full[4], full[5], full[6], full[7]);
+            ro[0] = make_float4(ring[0], ring[1], ring[2], ring[3]);
+            ro[1] = make_float4(ring[4], ring[5], ring[6], ring[7]);
+        }
+        __syncthreads();
+
+        // ---- column pass: 64 range bins x 8 groups of 4 Doppler cells; lanes along range ----
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int t = tid + it * kCfarNT;
+            const int x = t & 63, g = t >> 6;              // range bin in tile, Doppler group
+            const int r = r0 + x;
+            const float *fc = fullS + (4 * g) * RS + x;    // row index = Doppler offset + 6 relative to d0 + 4 g
+            const float *rc = ringS + (4 * g) * RS + x;
+            float fu[16], rg[8];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) fu[i] = (i < 7 || i > 8) ? fc[i * RS] : 0.f;   // full rows 0..6, 9..15
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rg[i] = rc[(i + 4) * RS];                       // ring rows 4..11
+            float f2[15], r2[7];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) f2[i] = fu[i] + fu[i + 1];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) r2[i] = rg[i] + rg[i + 1];
+            const int n_full = min(r + 10, Sp - 1) - max(r - 10, 0) + 1;
+            const int n_guard = min(r + 2, Sp - 1) - max(r - 2, 0) + 1;
+            const int n = 13 * n_full - 5 * n_guard;
+            const float inv_n = 1.0f / (float)n;
+            uint32_t bits = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float top = f2[q] + f2[q + 2];                   // full rows q .. q+3      (Doppler offsets -6 .. -3)
+                const float bot = f2[q + 9] + f2[q + 11];              // full rows q+9 .. q+12   (offsets +3 .. +6)
+                const float gd = (r2[q] + r2[q + 2]) + rg[q + 4];      // ring rows q+4 .. q+8    (offsets -2 .. +2)
+                const float noise = ((top + bot) + gd) * inv_n;
+                const float cut = tile[(4 * g + q + 6) * tw_ + x + 12];
+                const bool hit = (r < Sp) && (cut > p.alpha * noise);
+                if (hit) {
+                    bits |= 1u << (4 * g + q);
+                    noise_map[((size_t)f * Cp + d0 + 4 * g + q) * Sp + r] = noise;      // sparse: hit cells only
+                }
+            }
+            if (bits) atomicOr(&words[x], bits);
+        }
+    } else {
+        // ---- generic geometry: run-time bounds, one cell at a time ----
+        for (int t = tid; t < th_ * kCfarRT; t += kCfarNT) {
+            const int j = t / kCfarRT, x = t % kCfarRT;
+            const float *c = tile + j * tw_ + x + (Lp - Wr);   // c[i] = offset (i - Wr)
+            float left = 0.f, right = 0.f, mid = 0.f;
+            for (int i = 0; i < Wr - Gr; ++i) left += c[i];
+            for (int i = Wr + Gr + 1; i <= 2 * Wr; ++i) right += c[i];
+            for (int i = Wr - Gr; i <= Wr + Gr; ++i) mid += c[i];
+            ringS[j * RS + x] = left + right;
+            fullS[j * RS + x] = (left + right) + mid;
+        }
+        __syncthreads();
+        for (int t = tid; t < kCfarDT * kCfarRT; t += kCfarNT) {
+            const int x = t % kCfarRT, dl = t / kCfarRT;
+            const int r = r0 + x;
+            float T = 0.f;
+            for (int jj = 0; jj <= 2 * Wd; ++jj) {
+                const float *src = (jj >= Wd - Gd && jj <= Wd + Gd) ? ringS : fullS;
+                T += src[(dl + jj) * RS + x];
+            }
+            const int n_full = min(r + Wr, Sp - 1) - max(r - Wr, 0) + 1;
+            const int n_guard = min(r + Gr, Sp - 1) - max(r - Gr, 0) + 1;
+            const int n = (2 * Wd + 1) * n_full - (2 * Gd + 1) * n_guard;
+            const float noise = T * (1.0f / (float)max(n, 1));
+            const float cut = tile[(dl + Wd) * tw_ + x + Lp];
+            if ((r < Sp) && (n > 0) && (cut > p.alpha * noise)) {
+                atomicOr(&words[x], 1u << dl);
+                noise_map[((size_t)f * Cp + d0 + dl) * Sp + r] = noise;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < kCfarRT && r0 + tid < Sp) mask[((size_t)f * (Cp / 32) + dblk) * Sp + r0 + tid] = words[tid];
+}
+
+// ---------------------------------------------------------------------------
+// K4a: ordered hit list per frame + batch-wide offsets (last CTA scans)
+// ---------------------------------------------------------------------------
+constexpr int kListNT = 256;
+
+__global__ void __launch_bounds__(kListNT) list_kernel(PlanDev p, const uint32_t *__restrict__ mask, uint32_t *__restrict__ keys,
+                                                       uint32_t *__restrict__ counts, uint32_t *__restrict__ offsets,
+                                                       uint32_t *__restrict__ header, unsigned int *__restrict__ ticket,
+                                                       int n_frames, int dense_cap)
+{
+    __shared__ uint32_t scan[kListNT / 32], tsum[kListNT / 32];
+    __shared__ uint32_t total_s;
+    __shared__ bool is_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int f = blockIdx.x;
+    const int Sp = p.Sp, Cp = p.Cp;
+    const int wpr = Cp / 32;                                  // mask words per range bin
+    const int nwords = wpr * Sp;
+    const uint32_t *mf = mask + (size_t)f * nwords;
+    uint32_t *kf = keys + (size_t)f * p.max_det;
+
+    // thread t owns the contiguous run [i0, i1) of the (range, doppler-word) ordered word sequence
+    const int wpt = (nwords + kListNT - 1) / kListNT;
+    const int i0 = tid * wpt, i1 = min(nwords, i0 + wpt);
+    uint32_t cnt = 0;
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) cnt += __popc(mf[(size_t)(i % wpr) * Sp + i / wpr]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) scan[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < kListNT / 32; ++w) {
+            const uint32_t v = scan[w];
+            scan[w] = s;
+            s += v;
+        }
+        total_s = s;
+    }
+    __syncthreads();
+    uint32_t pos = scan[warp] + incl - cnt;
+    if (cnt) {
+        for (int i = i0; i < i1 && pos < (uint32_t)p.max_det; ++i) {
+            uint32_t w = mf[(size_t)(i % wpr) * Sp + i / wpr];
+            const uint32_t r = i / wpr, dbase = (i % wpr) * 32;
+            while (w && pos < (uint32_t)p.max_det) {
+                const int b = __ffs(w) - 1;
+                w &= w - 1;
+                kf[pos++] = (r << 16) | (dbase + b);
+            }
+        }
+    }
+    if (tid == 0) {
+        counts[f] = total_s;
+        __threadfence();
+        const unsigned int done = atomicAdd(ticket, 1u);
+        is_last = (done == (unsigned)n_frames - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+
+    // ---- last CTA: exclusive scan of the clipped counts -> offsets[f], header ----
+    __threadfence();
+    uint32_t carry = 0, true_total = 0;                        // uniform across the block
+    for (int base = 0; base < n_frames; base += kListNT) {
+        const int i = base + tid;
+        const uint32_t c = i < n_frames ? __ldcg(counts + i) : 0u;
+        const uint32_t cc = min(c, (uint32_t)p.max_det);
+        uint32_t inc = cc, ts = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        __syncthreads();                                       // scan[] / tsum[] free for reuse
+        if (lane == 31) { scan[warp] = inc; tsum[warp] = ts; }
+        __syncthreads();
+        uint32_t wbase = 0, chunk = 0, tchunk = 0;
+        for (int w = 0; w < kListNT / 32; ++w) {
+            if (w < warp) wbase += scan[w];
+            chunk += scan[w];
+            tchunk += tsum[w];
+        }
+        if (i < n_frames) offsets[i] = carry + wbase + inc - cc;
+        carry += chunk;
+        true_total += tchunk;
+    }
+    if (tid == 0) {
+        offsets[n_frames] = carry;
+        header[0] = min(carry, (uint32_t)dense_cap);
+        header[1] = true_total;
+        header[2] = (uint32_t)n_frames;
+        header[3] = (true_total != carry || carry > (uint32_t)dense_cap) ? 1u : 0u;
+        *ticket = 0u;                                           // self-cleaning for the next batch
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4b: one warp per detection of the batch
+// ---------------------------------------------------------------------------
+constexpr int kMeasNT = 256;
+constexpr int kMeasWarps = kMeasNT / 32;
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float2 *__restrict__ rs, const float2 *__restrict__ cube,
+                                                          const float *__restrict__ pmap, const float *__restrict__ noise_map,
+                                                          const uint32_t *__restrict__ mask, const uint32_t *__restrict__ keys,
+                                                          const uint32_t *__restrict__ offsets, mmw_detection *__restrict__ dense,
+                                                          int n_frames, int dense_cap)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2 *twa = reinterpret_cast<float2 *>(smem);                 // [n_theta]
+    float2 *xs = twa + p.n_theta;                                   // [warps][A]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Sp = p.Sp, Cp = p.Cp, A = p.A, C = p.C;
+    for (int i = tid; i < p.n_theta; i += kMeasNT) twa[i] = p.tw_a[i];
+    __syncthreads();
+
+    const uint32_t total = min(offsets[n_frames], (uint32_t)dense_cap);
+    float2 *xw = xs + warp * A;
+    const int nwarps = gridDim.x * kMeasWarps;
+    for (uint32_t g = blockIdx.x * kMeasWarps + warp; g < total; g += nwarps) {
+        // frame of detection g: largest f with offsets[f] <= g
+        int lo = 0, hi = n_frames - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        const int f = lo;
+        const uint32_t key = keys[(size_t)f * p.max_det + (g - offsets[f])];
+        const int r = key >> 16, d = key & 0xffff;
+        const float *pf = pmap + (size_t)f * Cp * Sp;
+        const uint32_t *mf = mask + (size_t)f * (Cp / 32) * Sp;
+        const float pw = pf[(size_t)d * Sp + r];
+        const float noise = noise_map[((size_t)f * Cp + d) * Sp + r];
+
+        // 3x3 grouping among detected cells (Doppler wraps, range clamps; ties -> lowest (r,d))
+        bool worse = false;
+        if (lane < 9 && lane != 4) {
+            const int rr = r + lane / 3 - 1;
+            const int dd = (d + lane % 3 - 1 + Cp) & (Cp - 1);
+            if (rr >= 0 && rr < Sp) {
+                const uint32_t w = mf[(size_t)(dd >> 5) * Sp + rr];
+                if ((w >> (dd & 31)) & 1u) {
+                    const float pn = pf[(size_t)dd * Sp + rr];
+                    const uint32_t kn = ((uint32_t)rr << 16) | (uint32_t)dd;
+                    worse = (pn > pw) || (pn == pw && kn < key);
+                }
+            }
+        }
+        const bool is_peak = __ballot_sync(0xffffffffu, worse) == 0u;
+
+        // antenna snapshot at (r, d)
+        if (cube != nullptr) {
+            for (int a = lane; a < A; a += 32) xw[a] = cube[(((size_t)f * A + a) * Cp + d) * Sp + r];
+        } else {
+            // fused mode: Doppler bin d of every antenna straight from the (already windowed) range spectrum
+            const float2 *src0 = rs + (((size_t)f * A) * Sp + r) * (size_t)C;
+            const size_t astride = (size_t)Sp * C;
+            int a = 0;
+            for (; a + 4 <= A; a += 4) {
+                float sx[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c = lane; c < C; c += 32) {
+                    const float2 w = p.tw_d[(c * d) & (Cp - 1)];
+                    float2 v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = src0[(a + q) * astride + c];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        sx[q] += v[q].x * w.x - v[q].y * w.y;
+                        sy[q] += v[q].x * w.y + v[q].y * w.x;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float tx = warp_sum(sx[q]), ty = warp_sum(sy[q]);
+                    if (lane == 0) xw[a + q] = make_float2(tx, ty);
+                }
+            }
+            for (; a < A; ++a) {
+                float sx = 0.f, sy = 0.f;
+                for (int c = lane; c < C; c += 32) {
+                    const float2 w = p.tw_d[(c * d) & (Cp - 1)];
+                    const float2 v = src0[a * astride + c];
+                    sx += v.x * w.x - v.y * w.y;
+                    sy += v.x * w.y + v.y * w.x;
+                }
+                sx = warp_sum(sx);
+                sy = warp_sum(sy);
+                if (lane == 0) xw[a] = make_float2(sx, sy);
+            }
+        }
+        __syncwarp();
+
+        // angle spectrum arg-max (strict >, first wins)
+        float best = -1.f;
+        int bestk = 0;
+        for (int k = lane; k < p.n_theta; k += 32) {
+            float yx = 0.f, yy = 0.f;
+            for (int a = 0; a < A; ++a) {
+                const float2 v = xw[a];
+                const float2 w = twa[(k * a) & (p.n_theta - 1)];
+                yx += v.x * w.x - v.y * w.y;
+                yy += v.x * w.y + v.y * w.x;
+            }
+            const float m = yx * yx + yy * yy;
+            if (m > best) { best = m; bestk = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+            if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int kw = bestk < p.n_theta / 2 ? bestk : bestk - p.n_theta;
+            float s = (float)kw * p.lambda_over_d / (float)p.n_theta;
+            s = fminf(1.f, fmaxf(-1.f, s));
+            mmw_detection o;
+            o.frame = (uint32_t)f + p.frame_offset;
+            o.range_bin = (uint16_t)r;
+            o.doppler_bin = (uint16_t)d;
+            o.power = pw;
+            o.noise = noise;
+            o.angle_bin = (int16_t)kw;
+            o.flags = is_peak ? MMW_FLAG_PEAK : 0;
+            o.angle_rad = asinf(s);
+            dense[g] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+static int cfar_smem_bytes(const PlanDev &p)
+{
+    const int tw_ = kCfarRT + 2 * ((p.win_r_half + 3) & ~3), th_ = kCfarDT + 2 * p.win_d_half;
+    return (th_ * tw_ + 2 * th_ * kCfarRS) * 4 + kCfarRT * 4;
+}
+
+cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, cudaStream_t st)
+{
+    const int bytes = cfar_smem_bytes(p);
+    const bool fixed = p.guard_r == 2 && p.guard_d == 2 && p.win_r_half == 10 && p.win_d_half == 6;
+    static int configured[2] = {0, 0};
+    if (bytes > configured[fixed]) {
+        cudaError_t e = fixed ? cudaFuncSetAttribute(cfar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+                              : cudaFuncSetAttribute(cfar_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        configured[fixed] = bytes;
+    }
+    dim3 grid((p.Sp + kCfarRT - 1) / kCfarRT, p.Cp / kCfarDT, n_frames);
+    if (fixed)
+        cfar_kernel<true><<<grid, kCfarNT, bytes, st>>>(p, pmap, mask, noise_map);
+    else
+        cfar_kernel<false><<<grid, kCfarNT, bytes, st>>>(p, pmap, mask, noise_map);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st)
+{
+    list_kernel<<<n_frames, kListNT, 0, st>>>(p, b.mask, b.keys, b.counts, b.offsets, b.header, b.ticket, n_frames, dense_cap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int bytes = p.n_theta * 8 + kMeasWarps * p.A * 8;
+    measure_kernel<<<sm_count * 4, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask, b.keys,
+                                                         b.offsets, b.dense, n_frames, dense_cap);
+    return cudaGetLastError();
+}
+
+}  // namespace mmw

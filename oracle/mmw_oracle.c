@@ -278,22 +278,45 @@ int orc_is_group_peak(const double *P, const uint8_t *mask, int Sp, int Cp, int 
     return 1;
 }
 
+typedef struct {
+    orc_cx *rs, *dc, *x;
+    double *P, *nz;
+    uint8_t *mask;
+} orc_scratch;
+
+static void scratch_alloc(orc_scratch *w, int Sp, int C, int Cp, int A)
+{
+    const long M = (long)Sp * Cp;
+    w->rs = (orc_cx *)malloc((size_t)A * Sp * C * sizeof(orc_cx));
+    w->dc = (orc_cx *)malloc((size_t)A * M * sizeof(orc_cx));
+    w->P = (double *)malloc((size_t)M * sizeof(double));
+    w->mask = (uint8_t *)malloc((size_t)M);
+    w->nz = (double *)malloc((size_t)M * sizeof(double));
+    w->x = (orc_cx *)malloc((size_t)A * sizeof(orc_cx));
+}
+
+static void scratch_free(orc_scratch *w)
+{
+    free(w->rs); free(w->dc); free(w->P); free(w->mask); free(w->nz); free(w->x);
+}
+
+/* one frame; per-thread scratch is reused across frames (the caller's optional output buffers win) */
 static long process_one(const int16_t *adc, int f, int S, int C, int A,
                         const float *win_r, const float *win_d,
                         const orc_cfar_params *p, double lambda_over_d,
-                        orc_detection *dets, long cap,
+                        orc_detection *dets, long cap, orc_scratch *w,
                         orc_cx *rs_out, orc_cx *dc_out, double *P_out,
                         uint8_t *mask_out, double *noise_out, long *total)
 {
     const int Sp = orc_next_pow2(S), Cp = orc_next_pow2(C);
     const long M = (long)Sp * Cp;
     const int n_theta = orc_angle_fft_size(A);
-    orc_cx *rs = rs_out ? rs_out : (orc_cx *)malloc((size_t)A * Sp * C * sizeof(orc_cx));
-    orc_cx *dc = dc_out ? dc_out : (orc_cx *)malloc((size_t)A * M * sizeof(orc_cx));
-    double *P = P_out ? P_out : (double *)malloc((size_t)M * sizeof(double));
-    uint8_t *mask = mask_out ? mask_out : (uint8_t *)malloc((size_t)M);
-    double *nz = noise_out ? noise_out : (double *)malloc((size_t)M * sizeof(double));
-    orc_cx *x = (orc_cx *)malloc((size_t)A * sizeof(orc_cx));
+    orc_cx *rs = rs_out ? rs_out : w->rs;
+    orc_cx *dc = dc_out ? dc_out : w->dc;
+    double *P = P_out ? P_out : w->P;
+    uint8_t *mask = mask_out ? mask_out : w->mask;
+    double *nz = noise_out ? noise_out : w->nz;
+    orc_cx *x = w->x;
 
     orc_range_fft(adc, S, C, A, win_r, rs);
     orc_doppler_fft(rs, Sp, C, A, win_d, dc);
@@ -321,12 +344,6 @@ static long process_one(const int16_t *adc, int f, int S, int C, int A,
             o->angle_rad = (float)orc_angle_rad(kw, n_theta, lambda_over_d);
         }
     *total = tot;
-    free(x);
-    if (!rs_out) free(rs);
-    if (!dc_out) free(dc);
-    if (!P_out) free(P);
-    if (!mask_out) free(mask);
-    if (!noise_out) free(nz);
     return n;
 }
 
@@ -345,18 +362,26 @@ long orc_process_frames(const int16_t *adc, int n_frames, int S, int C, int A,
     const long per = n_frames > 0 ? det_cap / n_frames : 0;
     long *cnt = (long *)calloc((size_t)(n_frames > 0 ? n_frames : 1), sizeof(long));
     long *tot = (long *)calloc((size_t)(n_frames > 0 ? n_frames : 1), sizeof(long));
-#ifdef _OPENMP
     if (n_threads < 1) n_threads = 1;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads)
 #endif
-    for (int f = 0; f < n_frames; ++f)
-        cnt[f] = process_one(adc + (long)f * frame_shorts, f, S, C, A, win_r, win_d, p,
-                             lambda_over_d, dets + (long)f * per, per,
-                             rs_out ? rs_out + (long)f * A * Sp * C : NULL,
-                             dc_out ? dc_out + (long)f * A * M : NULL,
-                             P_out ? P_out + (long)f * M : NULL,
-                             mask_out ? mask_out + (long)f * M : NULL,
-                             noise_out ? noise_out + (long)f * M : NULL, &tot[f]);
+    {
+        orc_scratch w;
+        scratch_alloc(&w, Sp, C, Cp, A);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int f = 0; f < n_frames; ++f)
+            cnt[f] = process_one(adc + (long)f * frame_shorts, f, S, C, A, win_r, win_d, p,
+                                 lambda_over_d, dets + (long)f * per, per, &w,
+                                 rs_out ? rs_out + (long)f * A * Sp * C : NULL,
+                                 dc_out ? dc_out + (long)f * A * M : NULL,
+                                 P_out ? P_out + (long)f * M : NULL,
+                                 mask_out ? mask_out + (long)f * M : NULL,
+                                 noise_out ? noise_out + (long)f * M : NULL, &tot[f]);
+        scratch_free(&w);
+    }
     long n = 0, t = 0;
     for (int f = 0; f < n_frames; ++f) {
         if (n != (long)f * per && cnt[f] > 0)
