@@ -56,31 +56,38 @@ __host__ __device__ constexpr int ilog2(int n)
     return l;
 }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex add / subtract are single packed-fp32 instructions on sm_100 (FADD2 / FFMA2): a float2 lives in
+// an aligned register pair, so one issue slot does both components.  The FFT kernels are issue-bound,
+// not FP-pipe-bound, so this is worth ~1/3 of the butterfly instruction count.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }   // exact: a - b
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 w)
 {
     return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
 }
 
-// a * exp(-j 2 pi K / 32), K in [0, 16), K known at compile time
+// (a - b) * exp(-j 2 pi K / 32), K in [0, 16), K known at compile time
 template <int K>
-__device__ __forceinline__ float2 mul_w32(float2 a)
+__device__ __forceinline__ float2 sub_mul_w32(float2 a, float2 b)
 {
     if constexpr (K == 0) {
-        return a;
-    } else if constexpr (K == 8) {                       // -j
-        return make_float2(a.y, -a.x);
-    } else if constexpr (K == 4) {                       // (1 - j)/sqrt2
+        return csub(a, b);
+    } else if constexpr (K == 8) {                       // * -j : (d.y, -d.x)
+        return make_float2(a.y - b.y, b.x - a.x);
+    } else if constexpr (K == 4) {                       // * (1 - j)/sqrt2
         constexpr float h = 0.70710678118654752440f;
-        return make_float2((a.x + a.y) * h, (a.y - a.x) * h);
-    } else if constexpr (K == 12) {                      // (-1 - j)/sqrt2
+        const float2 d = csub(a, b);
+        return make_float2((d.x + d.y) * h, (d.y - d.x) * h);
+    } else if constexpr (K == 12) {                      // * (-1 - j)/sqrt2
         constexpr float h = 0.70710678118654752440f;
-        return make_float2((a.y - a.x) * h, -(a.x + a.y) * h);
+        const float2 d = csub(a, b);
+        return make_float2((d.y - d.x) * h, -(d.x + d.y) * h);
     } else {
         constexpr float c = w32_cos(K);
         constexpr float s = w32_sin(K);                  // w = c - j s
-        return make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
+        const float2 d = csub(a, b);
+        return make_float2(fmaf(d.x, c, d.y * s), fmaf(d.y, c, -d.x * s));
     }
 }
 
@@ -91,7 +98,7 @@ __device__ __forceinline__ void dif_level(float2 (&x)[RTOT])
     if constexpr (I < N / 2) {
         const float2 a = x[BASE + I], b = x[BASE + I + N / 2];
         x[BASE + I] = cadd(a, b);
-        x[BASE + I + N / 2] = mul_w32<I * (32 / N)>(csub(a, b));
+        x[BASE + I + N / 2] = sub_mul_w32<I * (32 / N)>(a, b);
         dif_level<N, BASE, I + 1, RTOT>(x);
     }
 }

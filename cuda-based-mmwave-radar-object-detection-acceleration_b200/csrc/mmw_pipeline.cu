@@ -57,7 +57,7 @@ struct RangeSmem {
 // PAIR: a thread runs butterflies n2 and n2+1 together (one 8-byte load yields both samples of an IIQQ group).
 // PAD : n_samples < N (zero padding needs a bound check per load); CT: compile-time n_chirps, 0 = run time.
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT>
-__global__ void __launch_bounds__(NW * 32) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
+__global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
                                                             int n_tiles)
 {
     static_assert(R1 * R2 == N, "plan");
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(NW * 32) range_fft_kernel(PlanDev p, const int
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
                     const float2 v = y[bitrev(k2, LR2)];
-                    st_global_f2(o + (size_t)(R1 * k2) * C, make_float2(v.x * wdop, v.y * wdop));
+                    st_global_f2(o + (size_t)(R1 * k2) * C, cscale(v, wdop));
                 }
             }
         }
@@ -214,28 +214,33 @@ __global__ void __launch_bounds__(NW * 32) range_fft_kernel(PlanDev p, const int
 // ---------------------------------------------------------------------------
 // K2: Doppler FFT + non-coherent integration
 // ---------------------------------------------------------------------------
-template <int N, int BT>
+template <int N, int BT, int NSTAGE>
 struct DopplerSmem {
     static constexpr int kStageRow = N + 2;                          // float2 per staged row (16-byte multiple)
     static constexpr int kOffTw = 16;
     static constexpr int kOffStage = kOffTw + 8 * N;
     static constexpr int kStageBytes = BT * kStageRow * 8;
-    static constexpr int kOffWork = kOffStage + 2 * kStageBytes;
+    static constexpr int kOffWork = kOffStage + NSTAGE * kStageBytes;
     static constexpr int kBytes = kOffWork + BT * (N + 1) * 8;
 };
 
 // PAD: n_chirps < N.  SPT: compile-time Sp (range FFT length = stride of the power map / cube), 0 = run time.
-template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT>
-__global__ void __launch_bounds__(NW * 32) doppler_fft_kernel(PlanDev p, const float2 *__restrict__ rs, float2 *__restrict__ cube,
+// NSTAGE = 2: the next step is prefetched while the current one is transformed (double buffer);
+// NSTAGE = 1: one staging buffer, refilled behind pass 2 (smaller footprint -> more CTAs per SM).
+template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE>
+__global__ void __launch_bounds__(NW * 32, (2 * DopplerSmem<N, BT, NSTAGE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) doppler_fft_kernel(PlanDev p, const float2 *__restrict__ rs, float2 *__restrict__ cube,
                                                                float *__restrict__ pmap, int n_tiles)
 {
     static_assert(R1 * R2 == N, "plan");
-    using L = DopplerSmem<N, BT>;
+    using L = DopplerSmem<N, BT, NSTAGE>;
     constexpr int NT = NW * 32;
     constexpr int SUBS = 32 / BT;
     constexpr int NSLOT = NW * SUBS;
     constexpr int LR1 = ilog2(R1), LR2 = ilog2(R2);
     constexpr int UPS2 = (R1 + NSLOT - 1) / NSLOT;                   // pass-2 butterflies per slot
+    constexpr int UPS1 = (R2 + NSLOT - 1) / NSLOT;                   // pass-1 butterflies per slot
+    // a slot's pass-1 butterflies are the same for every step, so their twiddles can live in registers
+    constexpr bool TWREG = UPS1 * (R1 - 1) <= 16;
 
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);              // two barriers
@@ -252,7 +257,8 @@ __global__ void __launch_bounds__(NW * 32) doppler_fft_kernel(PlanDev p, const f
     // a "step" is one antenna of one tile; steps of consecutive tiles are pipelined back to back
     auto issue = [&](int tile, int a, int s) {
         const int rt = tile % nrt, f = tile / nrt;
-        uint64_t *b = &bar[s & 1];
+        const int buf = s % NSTAGE;
+        uint64_t *b = &bar[buf];
         if (lane == 0) {
             fence_proxy_async();
             mbar_arrive_expect_tx(b, (uint32_t)(BT * C * 8));
@@ -260,8 +266,12 @@ __global__ void __launch_bounds__(NW * 32) doppler_fft_kernel(PlanDev p, const f
         __syncwarp();
         if (lane < BT) {
             const float2 *src = rs + (((size_t)f * A + a) * Sp + rt * BT + lane) * (size_t)C;
-            bulk_g2s(stage + (size_t)(s & 1) * (BT * L::kStageRow) + lane * L::kStageRow, src, (uint32_t)(C * 8), b);
+            bulk_g2s(stage + (size_t)buf * (BT * L::kStageRow) + lane * L::kStageRow, src, (uint32_t)(C * 8), b);
         }
+    };
+    auto prefetch_next = [&](int tile, int a, int s) {                // the step after (tile, a), possibly of the next tile
+        if (a + 1 < A) issue(tile, a + 1, s + 1);
+        else if (tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, 0, s + 1);
     };
 
     if (tid == 0) {
@@ -277,6 +287,13 @@ __global__ void __launch_bounds__(NW * 32) doppler_fft_kernel(PlanDev p, const f
 
     float2 *wrow = work + row * (N + 1);
     int s = 0;                                                        // running step counter of this CTA
+    float2 twr[TWREG ? UPS1 : 1][TWREG ? R1 - 1 : 1];
+    if constexpr (TWREG) {
+#pragma unroll
+        for (int ui = 0; ui < UPS1; ++ui)
+#pragma unroll
+            for (int k1 = 1; k1 < R1; ++k1) twr[ui][k1 - 1] = tw[tw1_index(min(slot + ui * NSLOT, R2 - 1), k1, R1)];
+    }
 
 #pragma unroll 1
     for (; tile < n_tiles; tile += gridDim.x) {
@@ -290,34 +307,33 @@ __global__ void __launch_bounds__(NW * 32) doppler_fft_kernel(PlanDev p, const f
 
 #pragma unroll 1
         for (int a = 0; a < A; ++a, ++s) {
-            if (warp == 0) {                                          // prefetch the next step (possibly of the next tile)
-                if (a + 1 < A) issue(tile, a + 1, s + 1);
-                else if (tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, 0, s + 1);
-            }
-            mbar_wait(&bar[s & 1], (uint32_t)((s >> 1) & 1));
-            const float2 *srow = stage + (size_t)(s & 1) * (BT * L::kStageRow) + row * L::kStageRow;
+            if (NSTAGE == 2 && warp == 0) prefetch_next(tile, a, s);
+            mbar_wait(&bar[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+            const float2 *srow = stage + (size_t)(s % NSTAGE) * (BT * L::kStageRow) + row * L::kStageRow;
 
             // pass 1: R2 butterflies of radix R1 over stride R2 (Doppler window already applied by K1)
-#pragma unroll 1
-            for (int u = slot; u < R2; u += NSLOT) {
-                const int n2 = u;
-                float2 x[R1];
 #pragma unroll
-                for (int m = 0; m < R1; ++m) {
-                    const int n = n2 + m * R2;
-                    x[m] = (!PAD || n < C) ? srow[n] : make_float2(0.f, 0.f);
-                }
-                dft_regs<R1>(x);
-                const float2 *twu = tw + tw1_index(n2, 0, R1);
-                float2 *wo = wrow + n2;
+            for (int ui = 0; ui < UPS1; ++ui) {
+                const int n2 = slot + ui * NSLOT;
+                if (UPS1 * NSLOT == R2 || n2 < R2) {
+                    float2 x[R1];
 #pragma unroll
-                for (int k1 = 0; k1 < R1; ++k1) {
-                    float2 v = x[bitrev(k1, LR1)];
-                    if (k1 > 0) v = cmul(v, twu[2 * k1]);
-                    wo[k1 * R2] = v;
+                    for (int m = 0; m < R1; ++m) {
+                        const int n = n2 + m * R2;
+                        x[m] = (!PAD || n < C) ? srow[n] : make_float2(0.f, 0.f);
+                    }
+                    dft_regs<R1>(x);
+                    float2 *wo = wrow + n2;
+                    wo[0] = x[0];
+#pragma unroll
+                    for (int k1 = 1; k1 < R1; ++k1) {
+                        const float2 w = TWREG ? twr[ui][k1 - 1] : tw[tw1_index(n2, k1, R1)];
+                        wo[k1 * R2] = cmul(x[bitrev(k1, LR1)], w);
+                    }
                 }
             }
             __syncthreads();
+            if (NSTAGE == 1 && warp == 0) prefetch_next(tile, a, s);   // staging buffer consumed: refill behind pass 2
 
             // pass 2: radix R2 on contiguous runs; accumulate |X|^2 (ascending antenna order)
 #pragma unroll
@@ -440,11 +456,11 @@ static cudaError_t run_range(const PlanDev &p, const int16_t *adc, float2 *rs, i
     return run_range_t<N, R1, R2, BT, NW, PAIR, true, 0>(p, adc, rs, n_frames, st);
 }
 
-template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT>
+template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE>
 static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
-    auto k = doppler_fft_kernel<N, R1, R2, BT, NW, PAD, SPT>;
-    constexpr int bytes = DopplerSmem<N, BT>::kBytes;
+    auto k = doppler_fft_kernel<N, R1, R2, BT, NW, PAD, SPT, NSTAGE>;
+    constexpr int bytes = DopplerSmem<N, BT, NSTAGE>::kBytes;
     static int per_sm = 0;
     if (!per_sm) {
         cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
@@ -457,15 +473,21 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
     return cudaGetLastError();
 }
 
-template <int N, int R1, int R2, int BT, int NW, int SP0, int SP1>
+template <int N, int R1, int R2, int BT, int NW, int SP0, int SP1, int NSTAGE = 2>
 static cudaError_t run_doppler(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
     if (p.C == N) {
-        if (SP0 && p.Sp == SP0) return run_doppler_t<N, R1, R2, BT, NW, false, SP0>(p, rs, cube, pmap, n_frames, st);
-        if (SP1 && p.Sp == SP1) return run_doppler_t<N, R1, R2, BT, NW, false, SP1>(p, rs, cube, pmap, n_frames, st);
-        return run_doppler_t<N, R1, R2, BT, NW, false, 0>(p, rs, cube, pmap, n_frames, st);
+        if (SP0 && p.Sp == SP0) return run_doppler_t<N, R1, R2, BT, NW, false, SP0, NSTAGE>(p, rs, cube, pmap, n_frames, st);
+        if (SP1 && p.Sp == SP1) return run_doppler_t<N, R1, R2, BT, NW, false, SP1, NSTAGE>(p, rs, cube, pmap, n_frames, st);
+        return run_doppler_t<N, R1, R2, BT, NW, false, 0, NSTAGE>(p, rs, cube, pmap, n_frames, st);
     }
-    return run_doppler_t<N, R1, R2, BT, NW, true, 0>(p, rs, cube, pmap, n_frames, st);
+    return run_doppler_t<N, R1, R2, BT, NW, true, 0, NSTAGE>(p, rs, cube, pmap, n_frames, st);
+}
+
+static int variant(const char *name)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : 0;
 }
 
 bool plan_supported(int Sp, int Cp, const char **why)
@@ -495,8 +517,24 @@ cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube,
 {
     switch (p.Cp) {
     case 64:   return run_doppler<64, 8, 8, 16, 4, 0, 0>(p, rs, cube, pmap, n_frames, st);
-    case 128:  return run_doppler<128, 8, 16, 16, 4, 256, 128>(p, rs, cube, pmap, n_frames, st);
-    case 256:  return run_doppler<256, 16, 16, 16, 8, 512, 0>(p, rs, cube, pmap, n_frames, st);
+    case 128: {
+        const int v = variant("MMW_K2_VARIANT");
+        if (v == 1) return run_doppler<128, 8, 16, 8, 4, 256, 128, 2>(p, rs, cube, pmap, n_frames, st);
+        if (v == 2) return run_doppler<128, 8, 16, 16, 4, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
+        if (v == 3) return run_doppler<128, 8, 16, 8, 4, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
+        if (v == 4) return run_doppler<128, 8, 16, 16, 8, 256, 128, 2>(p, rs, cube, pmap, n_frames, st);
+        if (v == 5) return run_doppler<128, 8, 16, 32, 8, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
+        return run_doppler<128, 8, 16, 16, 4, 256, 128>(p, rs, cube, pmap, n_frames, st);
+    }
+    case 256: {
+        const int v = variant("MMW_K2_VARIANT");
+        if (v == 1) return run_doppler<256, 16, 16, 8, 4, 512, 0, 2>(p, rs, cube, pmap, n_frames, st);
+        if (v == 2) return run_doppler<256, 16, 16, 16, 8, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
+        if (v == 3) return run_doppler<256, 16, 16, 8, 4, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
+        if (v == 4) return run_doppler<256, 16, 16, 16, 4, 512, 0, 2>(p, rs, cube, pmap, n_frames, st);
+        if (v == 5) return run_doppler<256, 16, 16, 16, 4, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
+        return run_doppler<256, 16, 16, 16, 8, 512, 0>(p, rs, cube, pmap, n_frames, st);
+    }
     case 512:  return run_doppler<512, 16, 32, 16, 8, 1024, 0>(p, rs, cube, pmap, n_frames, st);
     case 1024: return run_doppler<1024, 32, 32, 8, 8, 0, 0>(p, rs, cube, pmap, n_frames, st);
     default:   return cudaErrorInvalidValue;

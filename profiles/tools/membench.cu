@@ -1,0 +1,106 @@
+// membench.cu — what HBM delivers on this B200 for the access patterns the radar kernels use:
+// read-only, write-only and copy streams with 128-bit LDG/STG, and a read-only stream staged through
+// shared memory by 1-D TMA bulk copies (the way K1/K2 load).  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__global__ void k_read(const int4 *__restrict__ in, size_t n, int4 *sink)
+{
+    int4 acc = make_int4(0, 0, 0, 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + i));
+        acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678) sink[0] = acc;
+}
+__global__ void k_write(int4 *__restrict__ out, size_t n)
+{
+    const int4 v = make_int4(1, 2, 3, 4);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
+}
+__global__ void k_copy(const int4 *__restrict__ in, int4 *__restrict__ out, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// each CTA streams CHUNK-byte pieces through a 2-deep ring of shared-memory buffers with cp.async.bulk
+template <int CHUNK>
+__global__ void k_tma_read(const char *__restrict__ in, size_t nchunks, int *sink)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ uint64_t bar[2];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    int acc = 0;
+    size_t c = blockIdx.x;
+    int s = 0;
+    auto issue = [&](size_t chunk, int st) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&bar[st & 1])), "r"(CHUNK));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(sm + (st & 1) * CHUNK)),
+                         "l"(in + chunk * CHUNK), "r"(CHUNK), "r"(s32(&bar[st & 1])));
+        }
+    };
+    if (c < nchunks) issue(c, 0);
+    for (; c < nchunks; c += gridDim.x, ++s) {
+        if (c + gridDim.x < nchunks) issue(c + gridDim.x, s + 1);
+        uint32_t done;
+        do {
+            asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p;}" : "=r"(done) : "r"(s32(&bar[s & 1])), "r"((s >> 1) & 1));
+        } while (!done);
+        acc ^= reinterpret_cast<const int *>(sm + (s & 1) * CHUNK)[threadIdx.x];
+        __syncthreads();
+    }
+    if (acc == 0x12345678) sink[0] = acc;
+}
+
+int main()
+{
+    const size_t bytes = 2048ull << 20;
+    char *a, *b;
+    cudaMalloc(&a, bytes);
+    cudaMalloc(&b, bytes);
+    cudaMemset(a, 1, bytes);
+    cudaMemset(b, 2, bytes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const size_t n = bytes / 16;
+    auto time = [&](const char *name, double moved, auto launch) {
+        float best = 1e9;
+        for (int it = 0; it < 6; ++it) {
+            cudaEventRecord(e0);
+            launch();
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (it > 0 && ms < best) best = ms;
+        }
+        printf("%-28s %8.3f ms  %8.1f GB/s   (%s)\n", name, best, moved / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+    };
+    for (int blocks : {148 * 4, 148 * 8, 148 * 16}) {
+        printf("grid %d x 512\n", blocks);
+        time("read  LDG.128", (double)bytes, [&] { k_read<<<blocks, 512>>>((const int4 *)a, n, (int4 *)b); });
+        time("write STG.128", (double)bytes, [&] { k_write<<<blocks, 512>>>((int4 *)b, n); });
+        time("copy  (read+write bytes)", 2.0 * bytes, [&] { k_copy<<<blocks, 512>>>((const int4 *)a, (int4 *)b, n); });
+    }
+    cudaFuncSetAttribute(k_tma_read<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(k_tma_read<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    for (int per_sm : {1, 2, 3}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "read  TMA bulk 32K x2, %d/SM", per_sm);
+        time(nm, (double)bytes, [&] { k_tma_read<32768><<<148 * per_sm, 256, 65536>>>(a, bytes / 32768, (int *)b); });
+    }
+    for (int per_sm : {2, 4, 6}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "read  TMA bulk 16K x2, %d/SM", per_sm);
+        time(nm, (double)bytes, [&] { k_tma_read<16384><<<148 * per_sm, 256, 32768>>>(a, bytes / 16384, (int *)b); });
+    }
+    return 0;
+}
