@@ -38,7 +38,7 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture under profiles/ (None until a capture for this exact build exists)
-NCU_TRAFFIC_BYTES = {"cfg3": None, "cfg2": None}
+NCU_TRAFFIC_BYTES = {"cfg3": None, "cfg2": None}      # filled from profiles/ncu_r1_*.md
 
 
 def peaks():
@@ -85,15 +85,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_fps(orc, pkg, S, C, A, cfg_id, n_frames, n_threads):
-    """frames/s of the plain-C oracle (fp64, radix-2, frame-parallel over n_threads) on n_frames frames."""
-    adc = pkg.synth.cube_batch(n_frames, S, C, A, cfg=cfg_id)
-    wr, wd = orc.hann_periodic(S), orc.hann_periodic(C)
-    orc.process_frames(adc[:1], 1, S, C, A, wr, wd)                       # touch code and pages
-    t0 = time.perf_counter()
-    out = orc.process_frames(adc, n_frames, S, C, A, wr, wd, n_threads=n_threads)
-    dt = time.perf_counter() - t0
-    return n_frames / dt, dt, int(out["n_total"])
+class CpuPort:
+    """The plain-C oracle (fp64, radix-2 FFTs, frame-parallel with OpenMP) as a CPU baseline: a fixed pool of
+    distinct synthetic frames of the workload, processed over and over until the requested amount of work is done."""
+
+    def __init__(self, orc, pkg, S, C, A, cfg_id, cores):
+        self.orc, self.S, self.C, self.A, self.cores = orc, S, C, A, cores
+        self.pool = pkg.synth.cube_batch(max(cores, 8), S, C, A, cfg=cfg_id)
+        self.wr, self.wd = orc.hann_periodic(S), orc.hann_periodic(C)
+        self.run(1)                                                      # touch code and pages
+
+    def run(self, passes):
+        """processes `passes` x pool frames; returns (frames, seconds, detections of the last pass)"""
+        n = self.pool.shape[0]
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            out = self.orc.process_frames(self.pool, n, self.S, self.C, self.A, self.wr, self.wd, n_threads=self.cores)
+        return passes * n, time.perf_counter() - t0, int(out["n_total"])
+
+    def passes_for(self, seconds):
+        n, dt, _ = self.run(1)
+        return max(1, int(round(seconds / max(dt, 1e-6))))
 
 
 def run_reference(args, rank, world):
@@ -106,11 +118,12 @@ def run_reference(args, rank, world):
     orc.build()
     S, C, A, _, cfg_idx = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    per_step = max(cores, 8) if args.workload == "cfg3" else 16 * max(cores, 8)
-    per_step = min(per_step, 256 if args.workload == "cfg3" else 4096)
+    port = CpuPort(orc, pkg, S, C, A, cfg_idx + 1, cores)
+    passes = port.passes_for(1.0)                                     # about one second of wall clock per step
+    per_step = passes * port.pool.shape[0]
     times = []
     for i in range(args.warmup + args.steps):
-        fps, dt, _ = cpu_port_fps(orc, pkg, S, C, A, cfg_idx + 1, per_step, cores)
+        _, dt, _ = port.run(passes)
         if i >= args.warmup:
             times.append(dt)
     T = float(np.sum(times))
@@ -174,15 +187,14 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     ctx.use_stream(stream.cuda_stream)
     dense_ptr, header_ptr = ctx.device_results()
-    dense_view = pkg.sharding.device_bytes_view(dense_ptr, 24 * F * ctx.max_det_per_frame, dev)
     header_view = pkg.sharding.device_bytes_view(header_ptr, 16, dev)
+    # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel
+    gather_records = min(F * ctx.max_det_per_frame, 16384)
+    gather = pkg.sharding.DetectionGather(ctx, dev, gather_records) if world > 1 else None
 
     def step():
         ctx.process_device(adc, F)
-        if world > 1:
-            n_local = header_view[:4].view(torch.int32).to(torch.int64)
-            return pkg.sharding.gather_detections(dense_view, n_local)
-        return None
+        return gather.run() if gather is not None else None
 
     def sync_all():
         torch.cuda.synchronize()
@@ -204,12 +216,18 @@ def main():
         e1.record(stream)
         sync_all()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    n_det_step = int(header_view[:4].view(torch.int32).item()) if world == 1 else (gathered.numel() // 24 if rank == 0 else 0)
+    if world == 1:
+        n_det_step, gather_overflow = int(header_view[:4].view(torch.int32).item()), 0
+    elif rank == 0:
+        recs, hdr = gather.read(pkg.DET_DTYPE)
+        n_det_step, gather_overflow = len(recs), int(hdr[3])
+        assert np.all(np.diff(recs["frame"].astype(np.int64)) >= 0) and int(hdr[2]) == world * F     # ordered, all frames accounted for
+    else:
+        n_det_step, gather_overflow = 0, 0
 
     # ---- per-stage device times (events between launches) for the roofline of the dominant kernel ----
     ctx.use_stream(None)
@@ -229,7 +247,6 @@ def main():
     achieved = stage_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
     b_alg = int(ctx.info.algorithmic_bytes_per_frame)
     fps = world * F * K / (ms * 1e-3)
-    pipeline_gbs = b_alg * F * K / (ms * 1e-3) / 1e9 / world * world   # per GPU: every rank moves b_alg * F per step
 
     # ---- end to end through the host-facing API: pinned host capture -> H2D -> chain -> D2H list ----
     host = torch.empty((F, ctx.frame_shorts), dtype=torch.int16, pin_memory=True)
@@ -249,6 +266,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_fps = world * F * e2e_steps / t_e2e
+    clocks = sampler.stop() if rank == 0 else None      # sampled every 200 ms from the timed region to the end of the e2e loop
 
     if rank == 0:
         line = {
@@ -258,7 +276,7 @@ def main():
             "config": {
                 "workload": f"{args.workload}: {S} samples x {C} chirps x {A} antennas, 2-D CA-CFAR (guard 2x2, train 8x4, alpha 15), "
                             f"{ctx.n_theta}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
-                "frames_per_gpu_per_step": F, "sharding": f"frame-sharded x{world}, detection lists gathered to rank 0",
+                "frames_per_gpu_per_step": F, "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel (overflow={gather_overflow})"),
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
                 "l2": f"inputs larger than L2: {F * 4 * N_adc / 1e6:.0f} MB int16 capture + {F * 8 * A * ctx.Sp * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
                 "detections_per_step": n_det_step,
@@ -275,17 +293,19 @@ def main():
             },
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": F * 4 * N_adc,
                     "d2h_bytes_per_step": 16 + 24 * len(dets), "steps": e2e_steps, "api": "mmw_process_host"},
-            "gpu_launches": K * ctx.info.kernels_per_batch,
+            "gpu_launches": K * (ctx.info.kernels_per_batch + (1 if world > 1 else 0)),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             orc = entry.load_oracle()
             orc.build()
             cores = os.cpu_count() or 1
-            n = max(cores, 8) if args.workload == "cfg3" else 16 * max(cores, 8)
-            v, dt, _ = cpu_port_fps(orc, pkg, S, C, A, cfg_idx + 1, min(n, 4096), cores)
-            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": f"{min(n, 4096)} frames of the same workload in {dt:.1f} s, plain-C fp64 oracle, {cores} threads"}
+            port = CpuPort(orc, pkg, S, C, A, cfg_idx + 1, cores)
+            passes = port.passes_for(12.0)                             # about 12 s of wall clock on all host cores
+            n, dt, _ = port.run(passes)
+            line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} frames ({port.pool.shape[0]} distinct, {passes} passes) of the same workload in {dt:.1f} s; "
+                                              f"plain-C fp64 oracle (the reference has no CPU code for these stages), {cores} OpenMP threads"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

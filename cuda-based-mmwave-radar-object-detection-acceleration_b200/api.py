@@ -16,6 +16,7 @@ from . import build as _build
 
 MMW_OK, MMW_ERR_ARG, MMW_ERR_CUDA, MMW_ERR_STATE, MMW_ERR_OVERFLOW = 0, -1, -2, -3, -4
 FLAG_PEAK = 1
+RESULT_HEADER_BYTES = 32
 
 DET_DTYPE = np.dtype(
     [
@@ -36,7 +37,7 @@ C_ABI_SYMBOLS = [
     "mmw_default_config", "mmw_create", "mmw_destroy", "mmw_last_error", "mmw_get_info",
     "mmw_set_windows", "mmw_get_windows", "mmw_set_frame_offset", "mmw_stream", "mmw_use_stream",
     "mmw_process_device", "mmw_process_host", "mmw_read_detections", "mmw_read_counts",
-    "mmw_device_results", "mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map",
+    "mmw_device_results", "mmw_device_result_block", "mmw_merge_gathered", "mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map",
     "mmw_copy_cfar_mask", "mmw_time_device",
     "mmw_legacy_process_frame", "mmw_legacy_process_frames", "mmw_legacy_copy_spectrum", "mmw_legacy_shutdown",
 ]
@@ -103,6 +104,8 @@ def load(build_if_missing: bool = True):
     L.mmw_read_detections.argtypes = [vp, vp, C.c_int, ip]
     L.mmw_read_counts.argtypes = [vp, vp, C.c_int]
     L.mmw_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.mmw_device_result_block.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
+    L.mmw_merge_gathered.argtypes = [vp, vp, C.c_int, C.c_longlong, vp, C.c_int]
     for name in ("mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map", "mmw_copy_cfar_mask"):
         getattr(L, name).argtypes = [vp, C.c_int, vp]
     L.mmw_time_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -255,6 +258,17 @@ class RadarContext:
         d, h = C.c_void_p(), C.c_void_p()
         _check(self._L.mmw_device_results(self._h, C.byref(d), C.byref(h)))
         return int(d.value), int(h.value)
+
+    def device_result_block(self):
+        """(device address, capacity in bytes) of the contiguous [32-byte header | dense records] block."""
+        b, n = C.c_void_p(), C.c_longlong(0)
+        _check(self._L.mmw_device_result_block(self._h, C.byref(b), C.byref(n)))
+        return int(b.value), int(n.value)
+
+    def merge_gathered(self, gathered_dev, n_ranks: int, stride_bytes: int, merged_dev, merged_capacity: int):
+        """rank 0: n_ranks gathered result blocks -> one merged block (asynchronous, one kernel)."""
+        _check(self._L.mmw_merge_gathered(self._h, C.c_void_p(_dev_ptr(gathered_dev)), n_ranks, stride_bytes,
+                                          C.c_void_p(_dev_ptr(merged_dev)), merged_capacity))
 
     # -- intermediates (canonical layouts)
     def range_spectrum(self, frame: int) -> np.ndarray:

@@ -35,6 +35,9 @@ static int next_pow2(int n)
 
 using namespace mmw;
 
+constexpr int kMaxChunks = 32;
+constexpr int kResultHeaderBytes = MMW_RESULT_HEADER_BYTES;
+
 struct mmw_ctx {
     mmw_config cfg;
     PlanDev plan;
@@ -56,13 +59,18 @@ struct mmw_ctx {
     uint32_t *d_counts;
     uint32_t *d_offsets;
     unsigned int *d_ticket;
+    unsigned char *d_result;  // [32-byte header | dense ordered detection list]: one D2H usually moves both
     mmw_detection *d_dense;
     uint32_t *d_header;
     void *d_scratch;         // export scratch
     size_t scratch_bytes;
     // pinned host
+    unsigned char *h_result;  // pinned mirror of d_result
     uint32_t *h_header;
     mmw_detection *h_dense;
+    uint32_t guess_det;       // records fetched speculatively with the header (adapts to the last batch)
+    cudaStream_t copy_stream; // H2D of host captures, overlapped chunk-wise with the kernels
+    cudaEvent_t chunk_ev[kMaxChunks];
     int dense_cap;
     int last_frames;
     size_t workspace_bytes;
@@ -147,9 +155,10 @@ void mmw_destroy(mmw_ctx *c)
     cudaSetDevice(c->device);
     cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
     cudaFree(c->d_adc); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_mask);
-    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_dense); cudaFree(c->d_header); cudaFree(c->d_scratch);
-    if (c->h_header) cudaFreeHost(c->h_header);
-    if (c->h_dense) cudaFreeHost(c->h_dense);
+    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_scratch);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -221,10 +230,17 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     if ((rc = dev_alloc(c, &c->d_ticket, (size_t)1))) return fail(rc);
     if (cudaMemset(c->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     c->dense_cap = F * cfg->max_det_per_frame;
-    if ((rc = dev_alloc(c, &c->d_dense, (size_t)c->dense_cap))) return fail(rc);
-    if ((rc = dev_alloc(c, &c->d_header, (size_t)4))) return fail(rc);
-    if (cudaMallocHost((void **)&c->h_header, 16) != cudaSuccess ||
-        cudaMallocHost((void **)&c->h_dense, (size_t)c->dense_cap * sizeof(mmw_detection)) != cudaSuccess) {
+    const size_t result_bytes = kResultHeaderBytes + (size_t)c->dense_cap * sizeof(mmw_detection);
+    if ((rc = dev_alloc(c, &c->d_result, result_bytes))) return fail(rc);
+    c->d_header = reinterpret_cast<uint32_t *>(c->d_result);
+    c->d_dense = reinterpret_cast<mmw_detection *>(c->d_result + kResultHeaderBytes);
+    c->guess_det = 4096;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { set_last_error("cudaStreamCreate failed"); return fail(MMW_ERR_CUDA); }
+    for (auto &e : c->chunk_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { set_last_error("cudaEventCreate failed"); return fail(MMW_ERR_CUDA); }
+    if (cudaMallocHost((void **)&c->h_result, result_bytes) == cudaSuccess) {
+        c->h_header = reinterpret_cast<uint32_t *>(c->h_result);
+        c->h_dense = reinterpret_cast<mmw_detection *>(c->h_result + kResultHeaderBytes);
+    } else {
         set_last_error("cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(MMW_ERR_CUDA);
     }
@@ -301,25 +317,44 @@ int mmw_use_stream(mmw_ctx *c, void *cuda_stream)
     return MMW_OK;
 }
 
-static int run_batch(mmw_ctx *c, const int16_t *adc_dev, int n_frames, cudaEvent_t *stage_ev)
+// stages 1-3 on frames [first, first + n) of the batch (they are per-frame independent)
+static int run_front(mmw_ctx *c, const int16_t *adc_dev, int first, int n, cudaEvent_t *stage_ev)
 {
     const PlanDev &p = c->plan;
     cudaStream_t st = c->stream;
+    const size_t M = (size_t)p.Sp * p.Cp;
+    const int16_t *adc = adc_dev + (size_t)first * 2 * p.S * p.C * p.A;
+    float2 *rs = c->d_rs + (size_t)first * p.A * p.Sp * p.C;
+    float2 *cube = p.keep_cube ? c->d_cube + (size_t)first * p.A * M : nullptr;
     if (stage_ev) CK(cudaEventRecord(stage_ev[0], st));
-    CK(launch_range_fft(p, adc_dev, c->d_rs, n_frames, st));
+    CK(launch_range_fft(p, adc, rs, n, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[1], st));
-    CK(launch_doppler_fft(p, c->d_rs, p.keep_cube ? c->d_cube : nullptr, c->d_pmap, n_frames, st));
+    CK(launch_doppler_fft(p, rs, cube, c->d_pmap + (size_t)first * M, n, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[2], st));
-    CK(launch_cfar(p, c->d_pmap, c->d_mask, c->d_noise, n_frames, st));
+    CK(launch_cfar(p, c->d_pmap + (size_t)first * M, c->d_mask + (size_t)first * (M / 32), c->d_noise + (size_t)first * M, n, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[3], st));
+    return MMW_OK;
+}
+
+// stage 4 over the whole batch: ordered hit list, measurements, dense list + header
+static int run_back(mmw_ctx *c, int n_frames, cudaEvent_t *stage_ev)
+{
+    const PlanDev &p = c->plan;
     DetectBuffers b;
     b.rs = c->d_rs; b.cube = c->d_cube; b.pmap = c->d_pmap; b.noise_map = c->d_noise; b.mask = c->d_mask;
     b.keys = c->d_keys; b.counts = c->d_counts; b.offsets = c->d_offsets; b.header = c->d_header;
     b.ticket = c->d_ticket; b.dense = c->d_dense;
-    CK(launch_detect(p, b, n_frames, c->dense_cap, c->sm_count, st));
-    if (stage_ev) CK(cudaEventRecord(stage_ev[4], st));
+    CK(launch_detect(p, b, n_frames, c->dense_cap, c->sm_count, c->stream));
+    if (stage_ev) CK(cudaEventRecord(stage_ev[4], c->stream));
     c->last_frames = n_frames;
     return MMW_OK;
+}
+
+static int run_batch(mmw_ctx *c, const int16_t *adc_dev, int n_frames, cudaEvent_t *stage_ev)
+{
+    int rc = run_front(c, adc_dev, 0, n_frames, stage_ev);
+    if (rc) return rc;
+    return run_back(c, n_frames, stage_ev);
 }
 
 static int check_batch_args(mmw_ctx *c, const void *adc, int n_frames, const char *who)
@@ -341,19 +376,25 @@ int mmw_process_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
     return run_batch(c, adc_dev, n_frames, nullptr);
 }
 
+// One D2H brings the header and the first `guess_det` records; a second copy is needed only when
+// the batch produced more than that (the guess follows the previous batch).
 static int fetch_results(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)
 {
     cudaStream_t st = c->stream;
-    CK(cudaMemcpyAsync(c->h_header, c->d_header, 16, cudaMemcpyDeviceToHost, st));
+    uint32_t guess = c->guess_det < (uint32_t)c->dense_cap ? c->guess_det : (uint32_t)c->dense_cap;
+    CK(cudaMemcpyAsync(c->h_result, c->d_result, kResultHeaderBytes + (size_t)guess * sizeof(mmw_detection), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t n_written = c->h_header[0];
     uint32_t n = n_written;
     int rc = c->h_header[3] ? MMW_ERR_OVERFLOW : MMW_OK;
     if ((int)n > det_capacity) { n = det_capacity > 0 ? (uint32_t)det_capacity : 0; rc = MMW_ERR_OVERFLOW; }
+    if (n > guess) {
+        CK(cudaMemcpyAsync(c->h_dense + guess, c->d_dense + guess, (size_t)(n - guess) * sizeof(mmw_detection), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    c->guess_det = n_written + n_written / 4 + 256;
     if (n > 0) {
         if (!dets) { set_last_error("detections pointer is null"); return MMW_ERR_ARG; }
-        CK(cudaMemcpyAsync(c->h_dense, c->d_dense, (size_t)n * sizeof(mmw_detection), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
         memcpy(dets, c->h_dense, (size_t)n * sizeof(mmw_detection));
     }
     if (n_det) *n_det = (int)n;
@@ -367,13 +408,28 @@ int mmw_process_host(mmw_ctx *c, const int16_t *adc_host, int n_frames, mmw_dete
     int rc = check_batch_args(c, adc_host, n_frames, "mmw_process_host");
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)n_frames * 4 * c->plan.S * c->plan.C * c->plan.A;
+    const size_t frame_shorts = (size_t)2 * c->plan.S * c->plan.C * c->plan.A;
     if (!c->d_adc) {            // staging for host captures, allocated on first use
-        rc = dev_alloc(c, &c->d_adc, (size_t)c->cfg.max_frames * 2 * c->plan.S * c->plan.C * c->plan.A);
+        rc = dev_alloc(c, &c->d_adc, (size_t)c->cfg.max_frames * frame_shorts);
         if (rc) return rc;
     }
-    CK(cudaMemcpyAsync(c->d_adc, adc_host, bytes, cudaMemcpyHostToDevice, c->stream));
-    rc = run_batch(c, c->d_adc, n_frames, nullptr);
+    // The capture goes up in chunks on a copy stream; stages 1-3 of chunk k run while chunk k+1 is still on
+    // the bus (frames are independent), stage 4 runs once over the whole batch.
+    const size_t frame_bytes = frame_shorts * sizeof(int16_t);
+    int chunk = (int)((48u << 20) / frame_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk * kMaxChunks < n_frames) chunk = (n_frames + kMaxChunks - 1) / kMaxChunks;
+    int k = 0;
+    for (int first = 0; first < n_frames; first += chunk, ++k) {
+        const int n = n_frames - first < chunk ? n_frames - first : chunk;
+        CK(cudaMemcpyAsync(c->d_adc + (size_t)first * frame_shorts, adc_host + (size_t)first * frame_shorts, (size_t)n * frame_bytes,
+                           cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->chunk_ev[k], c->copy_stream));
+        CK(cudaStreamWaitEvent(c->stream, c->chunk_ev[k], 0));
+        rc = run_front(c, c->d_adc, first, n, nullptr);
+        if (rc) return rc;
+    }
+    rc = run_back(c, n_frames, nullptr);
     if (rc) return rc;
     return fetch_results(c, dets, det_capacity, n_det);
 }
@@ -401,6 +457,26 @@ int mmw_device_results(mmw_ctx *c, const mmw_detection **dense_dets, const uint3
     if (!c) { set_last_error("mmw_device_results: null context"); return MMW_ERR_ARG; }
     if (dense_dets) *dense_dets = c->d_dense;
     if (header) *header = c->d_header;
+    return MMW_OK;
+}
+
+int mmw_device_result_block(mmw_ctx *c, const void **block, long long *capacity_bytes)
+{
+    if (!c) { set_last_error("mmw_device_result_block: null context"); return MMW_ERR_ARG; }
+    if (block) *block = c->d_result;
+    if (capacity_bytes) *capacity_bytes = kResultHeaderBytes + (long long)c->dense_cap * (long long)sizeof(mmw_detection);
+    return MMW_OK;
+}
+
+int mmw_merge_gathered(mmw_ctx *c, const void *gathered_dev, int n_ranks, long long stride_bytes, void *merged_dev, int merged_capacity)
+{
+    if (!c || !gathered_dev || !merged_dev) { set_last_error("mmw_merge_gathered: null argument"); return MMW_ERR_ARG; }
+    if (n_ranks < 1 || stride_bytes < kResultHeaderBytes || (stride_bytes % 8) != 0 || merged_capacity < 0) {
+        set_last_error("mmw_merge_gathered: bad rank count / stride / capacity");
+        return MMW_ERR_ARG;
+    }
+    CK(cudaSetDevice(c->device));
+    CK(launch_merge((const unsigned char *)gathered_dev, n_ranks, (size_t)stride_bytes, (unsigned char *)merged_dev, merged_capacity, c->stream));
     return MMW_OK;
 }
 

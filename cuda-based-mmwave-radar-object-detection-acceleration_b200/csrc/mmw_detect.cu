@@ -437,6 +437,52 @@ __global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float
 }
 
 // ---------------------------------------------------------------------------
+// merge of gathered per-rank result blocks (rank 0, after the NCCL gather)
+// ---------------------------------------------------------------------------
+constexpr int kMergeSplit = 8;       // CTAs per rank
+
+__global__ void __launch_bounds__(256) merge_kernel(const unsigned char *__restrict__ gathered, int n_ranks, size_t stride_bytes,
+                                                    unsigned char *__restrict__ merged, int merged_cap)
+{
+    const int r = blockIdx.x, part = blockIdx.y;
+    uint32_t off = 0, tot_written = 0, tot_true = 0, tot_frames = 0, ovf = 0;
+    for (int i = 0; i < n_ranks; ++i) {
+        const uint32_t *hd = reinterpret_cast<const uint32_t *>(gathered + (size_t)i * stride_bytes);
+        const uint32_t cap_i = (uint32_t)((stride_bytes - MMW_RESULT_HEADER_BYTES) / sizeof(mmw_detection));
+        const uint32_t n = min(hd[0], cap_i);
+        if (i < r) off += n;
+        tot_written += n;
+        tot_true += hd[1];
+        tot_frames += hd[2];
+        ovf |= hd[3] | (hd[0] > cap_i ? 1u : 0u);
+    }
+    const uint32_t *hd = reinterpret_cast<const uint32_t *>(gathered + (size_t)r * stride_bytes);
+    const uint32_t cap_r = (uint32_t)((stride_bytes - MMW_RESULT_HEADER_BYTES) / sizeof(mmw_detection));
+    const uint32_t n = min(hd[0], cap_r);
+    // 24-byte records as three 8-byte words
+    const uint2 *src = reinterpret_cast<const uint2 *>(gathered + (size_t)r * stride_bytes + MMW_RESULT_HEADER_BYTES);
+    uint2 *dst = reinterpret_cast<uint2 *>(merged + MMW_RESULT_HEADER_BYTES);
+    for (uint32_t i = part * 256 + threadIdx.x; i < 3 * n; i += kMergeSplit * 256) {
+        const uint32_t rec = off + i / 3;
+        if (rec < (uint32_t)merged_cap) dst[(size_t)off * 3 + i] = src[i];
+    }
+    if (r == 0 && part == 0 && threadIdx.x == 0) {
+        uint32_t *out = reinterpret_cast<uint32_t *>(merged);
+        out[0] = min(tot_written, (uint32_t)merged_cap);
+        out[1] = tot_true;
+        out[2] = tot_frames;
+        out[3] = (ovf || tot_written > (uint32_t)merged_cap) ? 1u : 0u;
+    }
+}
+
+cudaError_t launch_merge(const unsigned char *gathered, int n_ranks, size_t stride_bytes, unsigned char *merged, int merged_cap,
+                         cudaStream_t st)
+{
+    merge_kernel<<<dim3(n_ranks, kMergeSplit), 256, 0, st>>>(gathered, n_ranks, stride_bytes, merged, merged_cap);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 static int cfar_smem_bytes(const PlanDev &p)

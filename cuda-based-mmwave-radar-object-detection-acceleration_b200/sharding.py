@@ -74,6 +74,53 @@ def gather_detections(local_records, n_local, group=None):
     return out
 
 
+class DetectionGather:
+    """The exchange step of the sharded chain without a host round trip.
+
+    Every rank contributes a FIXED-size prefix of its contiguous result block ([32-byte header | ordered
+    records], mmw_device_result_block) — `records_per_rank` records, a few hundred KB — so the sizes NCCL needs
+    are known up front and nothing has to be copied to the host first.  Rank 0 receives the blocks in rank order
+    with one gather over NVLink and packs them into one ordered list with one launch of the library's merge
+    kernel (mmw_merge_gathered), reading the true counts from the gathered headers on the device.  A rank that
+    produced more than `records_per_rank` detections is truncated and the merged header's overflow word is set.
+    Everything is asynchronous on the context's stream (which must be torch's current stream)."""
+
+    def __init__(self, ctx, device, records_per_rank: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.ctx, self.group = ctx, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        block, cap_bytes = ctx.device_result_block()
+        self.stride = 32 + REC_BYTES * records_per_rank
+        if self.stride > cap_bytes:
+            raise ValueError("records_per_rank exceeds the context's detection capacity")
+        self.local = device_bytes_view(block, self.stride, device)
+        self.merged_cap = self.world * records_per_rank
+        if self.rank == 0:
+            self.gathered = torch.empty((self.world, self.stride), dtype=torch.uint8, device=device)
+            self.slots = list(self.gathered.unbind(0))
+            self.merged = torch.empty(32 + REC_BYTES * self.merged_cap, dtype=torch.uint8, device=device)
+
+    def run(self):
+        """call after ctx.process_device(); returns the merged block (torch.uint8, device) on rank 0, None elsewhere"""
+        import torch.distributed as dist
+
+        dst = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        dist.gather(self.local, gather_list=self.slots if self.rank == 0 else None, dst=dst, group=self.group)
+        if self.rank != 0:
+            return None
+        self.ctx.merge_gathered(self.gathered, self.world, self.stride, self.merged, self.merged_cap)
+        return self.merged
+
+    def read(self, det_dtype):
+        """rank 0: (records, header) of the last merged block on the host (synchronises)"""
+        m = self.merged.cpu().numpy()
+        header = m[:32].view(np.uint32).copy()
+        n = int(header[0])
+        return np.frombuffer(m[32:32 + REC_BYTES * n].tobytes(), dtype=det_dtype), header
+
+
 def records_from_bytes(buf, det_dtype) -> np.ndarray:
     """torch.uint8 tensor (any device) -> numpy structured array of detections."""
     return np.frombuffer(buf.cpu().numpy().tobytes(), dtype=det_dtype)

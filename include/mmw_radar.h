@@ -123,6 +123,18 @@ int mmw_read_counts(mmw_ctx *ctx, uint32_t *counts, int n_frames);
  * uint32 n_frames, uint32 overflow}. Valid until the next process call. */
 int mmw_device_results(mmw_ctx *ctx, const mmw_detection **dense_dets, const uint32_t **header);
 
+/* The header and the dense list are one contiguous device block: MMW_RESULT_HEADER_BYTES bytes of header
+ * {uint32 n_written, n_total, n_frames, overflow, 4 x reserved} followed by the records.  A fixed-size prefix of
+ * this block is what a multi-GPU gather sends (no host round trip to learn the count first). */
+#define MMW_RESULT_HEADER_BYTES 32
+int mmw_device_result_block(mmw_ctx *ctx, const void **block, long long *capacity_bytes);
+/* Rank-0 side of the gather: `gathered_dev` holds n_ranks result blocks (header + records) at a stride of
+ * stride_bytes, in rank order (= frame order).  Writes one merged block (header + all records, still ordered by
+ * (frame, range, doppler)) to merged_dev, which can hold merged_capacity records.  Asynchronous on the context
+ * stream; one kernel. */
+int mmw_merge_gathered(mmw_ctx *ctx, const void *gathered_dev, int n_ranks, long long stride_bytes,
+                       void *merged_dev, int merged_capacity);
+
 /* Intermediates of one frame of the last batch, copied to the host in canonical layouts
  * (synchronous, not on the hot path):
  *   range spectrum [A][Sp][C]  complex64 — NOTE: already multiplied by the Doppler window w_d[c]

@@ -95,3 +95,42 @@ def test_device_resident_path_and_stream(pkg, batches):
         ctx.use_stream(None)
         ms = ctx.time_device(dev, F, 2)
         assert ms > 0
+
+
+def test_merge_of_gathered_rank_blocks_equals_unsharded(pkg, batches):
+    """the rank-0 merge kernel (mmw_merge_gathered) on blocks produced by 3 emulated ranks == the 1-rank list"""
+    import torch
+
+    S, C, A, F = FULL[0]
+    adc = batches[(S, C, A)]
+    dev = torch.device("cuda", 0)
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        whole, _ = ctx.process_host(adc, F)
+    world, per_rank = 3, 4096
+    stride = 32 + 24 * per_rank
+    gathered = torch.zeros((world, stride), dtype=torch.uint8, device=dev)
+    ctxs = []
+    for rank in range(world):
+        first, cnt = pkg.sharding.shard_frames(F, world, rank)
+        c = pkg.RadarContext(S, C, A, cnt)
+        c.set_frame_offset(first)
+        c.process_device(torch.from_numpy(adc[first:first + cnt]).cuda(), cnt)
+        c.read_detections()                                       # synchronise
+        block, cap = c.device_result_block()
+        gathered[rank].copy_(pkg.sharding.device_bytes_view(block, stride, dev))
+        ctxs.append(c)
+    merged = torch.zeros(32 + 24 * world * per_rank, dtype=torch.uint8, device=dev)
+    ctxs[0].merge_gathered(gathered, world, stride, merged, world * per_rank)
+    torch.cuda.synchronize()
+    m = merged.cpu().numpy()
+    hdr = m[:32].view(np.uint32)
+    assert hdr[0] == len(whole) and hdr[2] == F and hdr[3] == 0
+    assert m[32:32 + 24 * len(whole)].tobytes() == whole.tobytes()
+    # a merged buffer that is too small truncates in order and raises the overflow word
+    small = torch.zeros(32 + 24 * 100, dtype=torch.uint8, device=dev)
+    ctxs[0].merge_gathered(gathered, world, stride, small, 100)
+    torch.cuda.synchronize()
+    s = small.cpu().numpy()
+    assert s[:32].view(np.uint32)[0] == 100 and s[:32].view(np.uint32)[3] == 1 and s[32:].tobytes() == whole[:100].tobytes()
+    for c in ctxs:
+        c.close()
