@@ -44,24 +44,26 @@ void plan_radices(int n, int *r1, int *r2)
 // ---------------------------------------------------------------------------
 // K1: range FFT
 // ---------------------------------------------------------------------------
-template <int N, int BT>
+template <int N, int BT, int NSTAGE>
 struct RangeSmem {
     static constexpr int kStageStride = 4 * N + 16;                 // bytes per staged int16 row
     static constexpr int kOffTw = 16;
     static constexpr int kOffWin = kOffTw + 8 * N;
     static constexpr int kOffStage = kOffWin + 4 * N;
-    static constexpr int kOffWork = kOffStage + BT * kStageStride;
+    static constexpr int kStageBytes = BT * kStageStride;
+    static constexpr int kOffWork = kOffStage + NSTAGE * kStageBytes;
     static constexpr int kBytes = kOffWork + BT * (N + 1) * 8;
 };
 
 // PAIR: a thread runs butterflies n2 and n2+1 together (one 8-byte load yields both samples of an IIQQ group).
 // PAD : n_samples < N (zero padding needs a bound check per load); CT: compile-time n_chirps, 0 = run time.
-template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT>
-__global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
+// NSTAGE = 1: one staging buffer, refilled behind pass 2; NSTAGE = 2: double buffer, refilled a whole tile ahead.
+template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE>
+__global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
                                                             int n_tiles)
 {
     static_assert(R1 * R2 == N, "plan");
-    using L = RangeSmem<N, BT>;
+    using L = RangeSmem<N, BT, NSTAGE>;
     constexpr int NT = NW * 32;
     constexpr int SUBS = 32 / BT;
     constexpr int NSLOT = NW * SUBS;
@@ -80,45 +82,47 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT>::kBytes <= 226 
     const int C = CT ? CT : p.C;
     const int nct = (C + BT - 1) / BT;
 
-    auto issue = [&](int tile) {            // warp 0: stage the BT int16 rows of `tile`
+    auto issue = [&](int tile, int it) {    // warp 0: stage the BT int16 rows of `tile` (the it-th tile of this CTA)
         const int ct = tile % nct, fa = tile / nct;
         const int a = fa % A, f = fa / A;
         const int c0 = ct * BT;
         const int nrows = min(BT, C - c0);
+        uint64_t *b = &bar[it % NSTAGE];
         if (lane == 0) {
             fence_proxy_async();
-            mbar_arrive_expect_tx(bar, (uint32_t)(nrows * S * 4));
+            mbar_arrive_expect_tx(b, (uint32_t)(nrows * S * 4));
         }
         __syncwarp();
         if (lane < nrows) {
             const int16_t *src = adc + (((size_t)f * C + c0 + lane) * A + a) * (size_t)(2 * S);
-            bulk_g2s(stage + lane * L::kStageStride, src, (uint32_t)(S * 4), bar);
+            bulk_g2s(stage + (it % NSTAGE) * L::kStageBytes + lane * L::kStageStride, src, (uint32_t)(S * 4), b);
         }
     };
 
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
     int tile = blockIdx.x;
-    if (warp == 0 && tile < n_tiles) issue(tile);
+    if (warp == 0 && tile < n_tiles) issue(tile, 0);
     for (int i = tid; i < N; i += NT) tw[i] = p.tw1_r[i];
     for (int i = tid; i < N; i += NT) win[i] = i < S ? p.win_r[i] : 0.f;
     __syncthreads();
 
-    const unsigned char *srow = stage + row * L::kStageStride;
     float2 *wrow = work + row * (N + 1);
-    uint32_t phase = 0;
+    int it = 0;                                                       // tiles done by this CTA
 
 #pragma unroll 1
-    for (; tile < n_tiles; tile += gridDim.x) {
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
         const int ct = tile % nct, fa = tile / nct;
         const int c0 = ct * BT;
         const bool row_ok = c0 + row < C;
         const float wdop = row_ok ? p.win_d[c0 + row] : 0.f;
-        mbar_wait(bar, phase);
-        phase ^= 1u;
+        if (NSTAGE == 2 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
+        mbar_wait(&bar[it % NSTAGE], (uint32_t)((it / NSTAGE) & 1));
+        const unsigned char *srow = stage + (it % NSTAGE) * L::kStageBytes + row * L::kStageStride;
 
         // ---- pass 1: R2 butterflies of radix R1 over stride R2, reading the staged int16 rows ----
         if constexpr (PAIR) {
@@ -185,8 +189,8 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT>::kBytes <= 226 
             }
         }
         __syncthreads();
-        // the staging buffer is consumed: prefetch the next tile behind pass 2
-        if (warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x);
+        // single staging buffer: it is consumed now, prefetch the next tile behind pass 2
+        if (NSTAGE == 1 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
 
         // ---- pass 2: R1 butterflies of radix R2 on contiguous runs; outputs go straight to HBM ----
         float2 *out = rs + (size_t)fa * (size_t)N * C + c0 + row;
@@ -426,11 +430,11 @@ static cudaError_t resident_ctas(K kernel, int threads, int smem_bytes, int *cta
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, threads, smem_bytes);
 }
 
-template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT>
+template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE>
 static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
-    auto k = range_fft_kernel<N, R1, R2, BT, NW, PAIR, PAD, CT>;
-    constexpr int bytes = RangeSmem<N, BT>::kBytes;
+    auto k = range_fft_kernel<N, R1, R2, BT, NW, PAIR, PAD, CT, NSTAGE>;
+    constexpr int bytes = RangeSmem<N, BT, NSTAGE>::kBytes;
     static int per_sm = 0;
     if (!per_sm) {
         cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
@@ -445,16 +449,18 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
 }
 
 // picks the PAD / compile-time-chirps specialisation
-template <int N, int R1, int R2, int BT, int NW, bool PAIR, int CT0, int CT1>
+template <int N, int R1, int R2, int BT, int NW, bool PAIR, int CT0, int CT1, int NSTAGE = 1>
 static cudaError_t run_range(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
     if (p.S == N) {
-        if (CT0 && p.C == CT0) return run_range_t<N, R1, R2, BT, NW, PAIR, false, CT0>(p, adc, rs, n_frames, st);
-        if (CT1 && p.C == CT1) return run_range_t<N, R1, R2, BT, NW, PAIR, false, CT1>(p, adc, rs, n_frames, st);
-        return run_range_t<N, R1, R2, BT, NW, PAIR, false, 0>(p, adc, rs, n_frames, st);
+        if (CT0 && p.C == CT0) return run_range_t<N, R1, R2, BT, NW, PAIR, false, CT0, NSTAGE>(p, adc, rs, n_frames, st);
+        if (CT1 && p.C == CT1) return run_range_t<N, R1, R2, BT, NW, PAIR, false, CT1, NSTAGE>(p, adc, rs, n_frames, st);
+        return run_range_t<N, R1, R2, BT, NW, PAIR, false, 0, NSTAGE>(p, adc, rs, n_frames, st);
     }
-    return run_range_t<N, R1, R2, BT, NW, PAIR, true, 0>(p, adc, rs, n_frames, st);
+    return run_range_t<N, R1, R2, BT, NW, PAIR, true, 0, NSTAGE>(p, adc, rs, n_frames, st);
 }
+
+static int variant(const char *name);
 
 template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE>
 static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
@@ -506,8 +512,20 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     switch (p.Sp) {
     case 64:   return run_range<64, 8, 8, 16, 4, true, 0, 0>(p, adc, rs, n_frames, st);
     case 128:  return run_range<128, 8, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
-    case 256:  return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
-    case 512:  return run_range<512, 16, 32, 16, 8, true, 256, 0>(p, adc, rs, n_frames, st);
+    case 256: {
+        const int v = variant("MMW_K1_VARIANT");
+        if (v == 1) return run_range<256, 16, 16, 8, 4, true, 128, 0, 2>(p, adc, rs, n_frames, st);
+        if (v == 2) return run_range<256, 16, 16, 16, 4, true, 128, 0, 2>(p, adc, rs, n_frames, st);
+        if (v == 3) return run_range<256, 16, 16, 8, 4, true, 128, 0, 1>(p, adc, rs, n_frames, st);
+        return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
+    }
+    case 512: {
+        const int v = variant("MMW_K1_VARIANT");
+        if (v == 1) return run_range<512, 16, 32, 8, 4, true, 256, 0, 2>(p, adc, rs, n_frames, st);
+        if (v == 2) return run_range<512, 16, 32, 16, 8, true, 256, 0, 2>(p, adc, rs, n_frames, st);
+        if (v == 3) return run_range<512, 16, 32, 8, 4, true, 256, 0, 1>(p, adc, rs, n_frames, st);
+        return run_range<512, 16, 32, 16, 8, true, 256, 0>(p, adc, rs, n_frames, st);
+    }
     case 1024: return run_range<1024, 32, 32, 16, 8, false, 512, 0>(p, adc, rs, n_frames, st);
     default:   return cudaErrorInvalidValue;
     }
