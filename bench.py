@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — radar frames/s (ADC cube -> detections) on N B200s, with roofline and CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg4|cfg5|cfg1] [--impl ours|reference]
 
 A step = one pass of the whole chain (range FFT -> Doppler FFT + |X|^2 integration -> 2-D CA-CFAR ->
 detection records incl. angle FFT + grouping -> dense list) over one batch of synthetic frames per GPU.
@@ -12,8 +12,13 @@ detection records incl. angle FFT + grouping -> dense list) over one batch of sy
   roofline      dominant kernel: algorithmic bytes per launch / CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline  the plain-C oracle (oracle/mmw_oracle.c, kind "port": the reference has no CPU code for
                 these stages) timed on the box's host cores on a bounded sample of the same workload
-Workloads (BASELINE.json configs): cfg3 = 512 samples x 256 chirps x 12 virtual antennas (the configuration
-north_star's >= 60 % roofline target is quoted on; default), cfg2 = 256 x 128 x 4, batch 1024.
+Workloads (BASELINE.json configs):
+  cfg3  512 samples x 256 chirps x 12 virtual antennas — the shape north_star's >= 60 % roofline target is quoted on (default)
+  cfg2  256 x 128 x 4, batch of 1024 frames (configs[1])
+  cfg4  1024 x 512 x 192 imaging cube, 4 frames per GPU per step (configs[3])
+  cfg5  64 sensors x (256 x 128 x 12): latency mode — every frame is its own call; p50/p99 per-frame latency (configs[4])
+  cfg1  the reference's own path (100 x 128 x 4, rx0, base-frame subtraction, one 16 384-point FFT, arg-max -> metres)
+        through the drop-in library; its CPU baseline is the reference's own code (oracle/_ref, kind "reference") (configs[0])
 """
 from __future__ import annotations
 
@@ -31,14 +36,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
+METRIC = "radar frames/sec (ADC cube->detections)"
 WORKLOADS = {
-    # name: (S, C, A, frames per GPU per step, BASELINE.json config index)
-    "cfg3": (512, 256, 12, 64, 2),
-    "cfg2": (256, 128, 4, 1024, 1),
+    # name: kind, S, C, A, frames per GPU per step, BASELINE.json config index
+    "cfg3": dict(kind="chain", S=512, C=256, A=12, F=64, idx=2),
+    "cfg2": dict(kind="chain", S=256, C=128, A=4, F=1024, idx=1),
+    "cfg4": dict(kind="chain", S=1024, C=512, A=192, F=4, idx=3),
+    "cfg5": dict(kind="stream", S=256, C=128, A=12, F=64, idx=4),
+    "cfg1": dict(kind="legacy", S=100, C=128, A=4, F=4096, idx=0),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` capture under profiles/ (None until a capture for this exact build exists)
-NCU_TRAFFIC_BYTES = {"cfg3": None, "cfg2": None}      # filled from profiles/ncu_r1_*.md
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the workload's batch size, from the
+# committed `ncu --set full` captures (profiles/ncu_r1_stages.md); None = no capture for that workload
+NCU_TRAFFIC_BYTES = {"cfg3": 1150343424, "cfg2": None, "cfg4": None, "cfg5": None, "cfg1": None}
 
 
 def peaks():
@@ -90,10 +99,13 @@ class CpuPort:
     distinct synthetic frames of the workload, processed over and over until the requested amount of work is done."""
 
     def __init__(self, orc, pkg, S, C, A, cfg_id, cores):
-        self.orc, self.S, self.C, self.A, self.cores = orc, S, C, A, cores
-        self.pool = pkg.synth.cube_batch(max(cores, 8), S, C, A, cfg=cfg_id)
+        big = S * C * A > 16 * 1024 * 1024                              # cfg4: 1.6 GB of fp64 scratch per thread
+        self.cores = min(cores, 2) if big else cores
+        self.orc, self.S, self.C, self.A = orc, S, C, A
+        self.pool = pkg.synth.cube_batch(2 if big else max(cores, 8), S, C, A, cfg=cfg_id)
         self.wr, self.wd = orc.hann_periodic(S), orc.hann_periodic(C)
-        self.run(1)                                                      # touch code and pages
+        if not big:
+            self.run(1)                                                  # touch code and pages
 
     def run(self, passes):
         """processes `passes` x pool frames; returns (frames, seconds, detections of the last pass)"""
@@ -108,82 +120,140 @@ class CpuPort:
         return max(1, int(round(seconds / max(dt, 1e-6))))
 
 
+class LegacyCpu:
+    """cfg1: the reference's own CPU loop body (oracle/_ref/libref_cpu.so, compiled from /root/reference: kind
+    "reference"), or the bit-identical oracle restatement where oracle/_ref was not built (kind "port").
+    Single-threaded like the reference."""
+
+    def __init__(self, orc, pkg):
+        self.orc = orc
+        self.cap = pkg.synth.legacy_capture(33, seed=0)
+        self.base = orc.reshape(self.cap[0], 100, 128, 4)[:12800]
+        self.kind = "reference" if orc.have_ref() else "port"
+
+    def run(self, passes):
+        t = 0.0
+        for _ in range(passes):
+            if self.kind == "reference":
+                dt, _ = self.orc.ref_cpu_time_frames(self.cap[1:], self.base)
+            else:
+                t0 = time.perf_counter()
+                for f in range(1, self.cap.shape[0]):
+                    self.orc.legacy_frame(self.cap[f], self.base)
+                dt = time.perf_counter() - t0
+            t += dt
+        return passes * (self.cap.shape[0] - 1), t
+
+    def passes_for(self, seconds):
+        n, dt = self.run(1)
+        return max(1, int(round(seconds / max(dt, 1e-6))))
+
+
+def workload_text(name):
+    w = WORKLOADS[name]
+    if w["kind"] == "legacy":
+        return (f"cfg1: reference path, 100 samples x 128 chirps x 4 rx per frame, rx0 - base frame, 16384-pt FFT, arg-max -> metres "
+                f"(BASELINE.json configs[{w['idx']}])")
+    return f"{name}: {w['S']} samples x {w['C']} chirps x {w['A']} antennas"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The reference has no CPU (or GPU)
-    code for the range/Doppler/CFAR/angle chain, so per north_star the plain-C oracle port
-    stands in (kind "port"), frame-parallel on all host cores, on a bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  cfg1: the reference's own
+    code (oracle/_ref).  Other workloads: the reference has no CPU (or GPU) code for the range/Doppler/CFAR/angle chain
+    (SURVEY.md §0), so per north_star the plain-C oracle port stands in (kind "port"), frame-parallel on all host cores."""
     if rank != 0:
         return
     pkg, orc = entry.load_package(), entry.load_oracle()
     orc.build()
-    S, C, A, _, cfg_idx = WORKLOADS[args.workload]
+    w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    port = CpuPort(orc, pkg, S, C, A, cfg_idx + 1, cores)
-    passes = port.passes_for(1.0)                                     # about one second of wall clock per step
-    per_step = passes * port.pool.shape[0]
-    times = []
+    if w["kind"] == "legacy":
+        port = LegacyCpu(orc, pkg)
+        passes, kind, used = port.passes_for(1.0), port.kind, 1
+        run = lambda: port.run(passes)[:2]                                  # noqa: E731
+        what = "the reference's own cpuTiming() loop body compiled from /root/reference" if kind == "reference" else "oracle restatement of the reference CPU loop"
+    else:
+        port = CpuPort(orc, pkg, w["S"], w["C"], w["A"], w["idx"] + 1, cores)
+        passes, kind, used = port.passes_for(1.0), "port", port.cores
+        run = lambda: port.run(passes)[:2]                                  # noqa: E731
+        what = "plain-C fp64 oracle (the reference has no CPU code for these stages)"
+    times, per_step = [], 0
     for i in range(args.warmup + args.steps):
-        _, dt, _ = port.run(passes)
+        per_step, dt = run()
         if i >= args.warmup:
             times.append(dt)
     T = float(np.sum(times))
     value = per_step * len(times) / T
     line = {
-        "impl": "reference", "metric": "radar frames/sec (ADC cube->detections)", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * T / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {S} samples x {C} chirps x {A} antennas, 2-D CA-CFAR, angle FFT "
-                               f"(BASELINE.json configs[{cfg_idx}])", "frames_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} frames per step x {len(times)} steps, plain-C fp64 oracle, {cores} threads"},
+        "config": {"workload": workload_text(args.workload) + (", 2-D CA-CFAR, angle FFT" if w["kind"] != "legacy" else "")
+                               + (f" (BASELINE.json configs[{w['idx']}])" if w["kind"] != "legacy" else ""),
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": used, "kind": kind,
+                         "sample": f"{per_step} frames per step x {len(times)} steps, {what}, {used} thread(s)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: workload's)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--keep-cube", action="store_true", help="materialise the Doppler cube in HBM (default: fused)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+class Env:
+    """torch / distributed / stdout plumbing shared by the three workload kinds"""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    import torch
-    import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", rank=self.rank, world_size=self.world, device_id=self.dev)
+        # keep stdout for the one JSON line: libraries (NCCL's version banner) write to fd 1 during init
+        self.real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        self.pkg = entry.load_package()
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    # keep stdout for the one JSON line: libraries (NCCL's version banner) write to fd 1 during init
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    pkg = entry.load_package()
-    S, C, A, F, cfg_idx = WORKLOADS[args.workload]
-    if args.frames:
-        F = args.frames
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def run_chain(args, env):
+    """cfg2 / cfg3 / cfg4: batches through the whole chain"""
+    torch, pkg, dev, rank, world = env.torch, env.pkg, env.dev, env.rank, env.world
+    w = WORKLOADS[args.workload]
+    S, C, A, F, cfg_idx = w["S"], w["C"], w["A"], args.frames or w["F"], w["idx"]
     K, W = args.steps, args.warmup
 
-    ctx = pkg.RadarContext(S, C, A, F, keep_doppler_cube=args.keep_cube, max_det_per_frame=4096, device=local_rank)
+    ctx = pkg.RadarContext(S, C, A, F, keep_doppler_cube=args.keep_cube, max_det_per_frame=4096, device=env.local_rank)
     first_frame = rank * F                                     # weak scaling: every rank owns F frames of the global batch
     ctx.set_frame_offset(first_frame)
     adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=cfg_idx + 1, first_frame=first_frame)
@@ -192,38 +262,35 @@ def main():
     ctx.use_stream(stream.cuda_stream)
     dense_ptr, header_ptr = ctx.device_results()
     header_view = pkg.sharding.device_bytes_view(header_ptr, 16, dev)
-    # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel
+    # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel,
+    # software-pipelined one step behind the compute (sharding.DetectionGather)
     gather_records = min(F * ctx.max_det_per_frame, 32768)
     gather = pkg.sharding.DetectionGather(ctx, dev, gather_records) if world > 1 else None
 
     def step():
         ctx.process_device(adc, F)
-        return gather.run() if gather is not None else None
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        if gather is not None:
+            gather.run()
 
     with torch.cuda.stream(stream):
         for _ in range(W):
             step()
-        sync_all()
-        sampler = ClockSampler(local_rank)
+        if gather is not None:
+            gather.flush()
+        env.sync_all()
+        sampler = ClockSampler(env.local_rank)
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(K):
-            gathered = step()
+            step()
+        if gather is not None:
+            gather.flush()                                  # the last step's gather + merge are inside the timed region
         e1.record(stream)
-        sync_all()
+        env.sync_all()
         ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = env.max_over_ranks(ms)
     frame_counts = ctx.read_counts(F)                       # true per-frame hit counts of this rank's last batch
     if world == 1:
         n_det_step, gather_overflow = int(header_view[:4].view(torch.int32).item()), 0
@@ -236,17 +303,17 @@ def main():
 
     # ---- per-stage device times (events between launches) for the roofline of the dominant kernel ----
     ctx.use_stream(None)
-    total_ms, stage_ms = ctx.time_device(adc, F, max(3, min(K, 10)), per_stage=True)
     iters = max(3, min(K, 10))
+    total_ms, stage_ms = ctx.time_device(adc, F, iters, per_stage=True)
     stage_ms = [s / iters for s in stage_ms]
     N_adc, N, M = S * C * A, ctx.Sp * ctx.Cp * A, ctx.Sp * ctx.Cp
     stage_bytes = [
         F * (4 * N_adc + 8 * A * ctx.Sp * C),                   # K1: int16 IQ in, range spectrum out
         F * (8 * A * ctx.Sp * C + (8 * N if args.keep_cube else 0) + 4 * M),   # K2: spectrum in, (cube +) power map out
         F * (4 * M + M // 8),                                   # K3: power map in, bit mask out
-        F * (M // 8),                                           # K4+K5: mask in (+ D records)
+        F * (M // 8),                                           # K4a+K4b: mask in (+ D records)
     ]
-    names = ["range_fft_kernel", "doppler_fft_kernel", "cfar_kernel", "detect_kernel+compact_kernel"]
+    names = ["range_fft_kernel", "doppler_fft_kernel", "cfar_kernel", "list_kernel+measure_kernel"]
     dom = int(np.argmax(stage_ms))
     peak, peak_src = peaks()
     achieved = stage_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
@@ -261,27 +328,25 @@ def main():
     e2e_steps = max(3, min(K, 10))
     for _ in range(2):
         dets, _ = ctx.process_host(host, F, out=out)
-    sync_all()
+    env.sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         dets, _ = ctx.process_host(host, F, out=out)
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+    t_e2e = env.max_over_ranks(time.perf_counter() - t0)
     e2e_fps = world * F * e2e_steps / t_e2e
     clocks = sampler.stop() if rank == 0 else None      # sampled every 200 ms from the timed region to the end of the e2e loop
 
     if rank == 0:
+        traffic = NCU_TRAFFIC_BYTES.get(args.workload) if (names[dom] == "range_fft_kernel" and F == w["F"] and not args.keep_cube) else None
         line = {
-            "metric": "radar frames/sec (ADC cube->detections)", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: {S} samples x {C} chirps x {A} antennas, 2-D CA-CFAR (guard 2x2, train 8x4, alpha 15), "
+                "workload": f"{workload_text(args.workload)}, 2-D CA-CFAR (guard 2x2, train 8x4, alpha 15), "
                             f"{ctx.n_theta}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
-                "frames_per_gpu_per_step": F, "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel (overflow={gather_overflow})"),
+                "frames_per_gpu_per_step": F,
+                "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel, pipelined one step behind the compute (overflow={gather_overflow})"),
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
                 "l2": f"inputs larger than L2: {F * 4 * N_adc / 1e6:.0f} MB int16 capture + {F * 8 * A * ctx.Sp * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
                 "detections_per_step": n_det_step, "max_detections_in_one_frame": int(frame_counts.max()),
@@ -289,16 +354,18 @@ def main():
             },
             "roofline": {
                 "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES.get(args.workload), "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stage_bytes[dom], "kernel_ms": stage_ms[dom],
                 "stage_ms": dict(zip(names, stage_ms)),
                 "stage_gbs": {n: (b / (t * 1e-3) / 1e9 if t > 0 else None) for n, b, t in zip(names, stage_bytes, stage_ms)},
                 "pipeline": {"algorithmic_bytes_per_frame": b_alg, "achieved": b_alg * F * K / (ms * 1e-3) / 1e9,
                              "frac": b_alg * F * K / (ms * 1e-3) / 1e9 / peak, "frac_of_8000_nominal": b_alg * F * K / (ms * 1e-3) / 1e9 / 8000.0,
-                             "note": "28N+8M bytes/frame (SURVEY.md 8d) x frames / step time, per GPU"},
+                             "moved_bytes_per_frame": sum(stage_bytes) // F, "moved_frac": sum(stage_bytes) * K / (ms * 1e-3) / 1e9 / peak,
+                             "note": "achieved/frac: 28N+8M bytes/frame (SURVEY.md 8d) x frames / step time, per GPU; moved_*: the bytes "
+                                     "the kernels of this build actually read and write (fused mode skips the cube)"},
             },
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": F * 4 * N_adc,
-                    "d2h_bytes_per_step": 16 + 24 * len(dets), "steps": e2e_steps, "api": "mmw_process_host"},
+                    "d2h_bytes_per_step": 32 + 24 * len(dets), "steps": e2e_steps, "api": "mmw_process_host"},
             "gpu_launches": K * (ctx.info.kernels_per_batch + (1 if world > 1 else 0)),
             "clocks": clocks,
         }
@@ -307,18 +374,222 @@ def main():
             orc.build()
             cores = os.cpu_count() or 1
             port = CpuPort(orc, pkg, S, C, A, cfg_idx + 1, cores)
-            passes = port.passes_for(12.0)                             # about 12 s of wall clock on all host cores
+            passes = port.passes_for(12.0)                             # about 12 s of wall clock on the host cores
             n, dt, _ = port.run(passes)
-            line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": port.cores, "kind": "port",
                                     "sample": f"{n} frames ({port.pool.shape[0]} distinct, {passes} passes) of the same workload in {dt:.1f} s; "
-                                              f"plain-C fp64 oracle (the reference has no CPU code for these stages), {cores} OpenMP threads"}
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        print(json.dumps(line), flush=True)
+                                              f"plain-C fp64 oracle (the reference has no CPU code for these stages), {port.cores} OpenMP threads"}
+        env.emit(line)
     ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+
+
+def run_stream(args, env):
+    """cfg5: 64 sensors x (256 x 128 x 12) at 30 fps — latency mode.  Every frame is its own call (a sensor's frame is
+    processed the moment it arrives); sensors are pinned to GPUs (sensor mod N).  A step = one tick = one frame from
+    every sensor of this rank."""
+    torch, pkg, dev, rank, world = env.torch, env.pkg, env.dev, env.rank, env.world
+    w = WORKLOADS[args.workload]
+    S, C, A, cfg_idx = w["S"], w["C"], w["A"], w["idx"]
+    sensors_total = args.frames or w["F"]
+    sensors = [s for s in range(sensors_total) if s % world == rank]
+    F = len(sensors)
+    K, W = args.steps, args.warmup
+    ctx = pkg.RadarContext(S, C, A, F, max_det_per_frame=4096, device=env.local_rank)
+    ctx.set_graph_mode(not args.no_graph)
+    adc = torch.stack([pkg.synth.cube_batch_torch(1, S, C, A, dev, cfg=cfg_idx + 1, first_frame=s)[0] for s in sensors])
+    host = torch.empty((F, ctx.frame_shorts), dtype=torch.int16, pin_memory=True)
+    host.copy_(adc)
+    torch.cuda.synchronize()
+    out = np.empty(ctx.max_det_per_frame, pkg.DET_DTYPE)
+    frames = [host[i] for i in range(F)]
+    dframes = [adc[i] for i in range(F)]
+
+    def tick_host(lat=None):
+        n = 0
+        for i in range(F):
+            t0 = time.perf_counter()
+            ctx.set_frame_offset(sensors[i])
+            dets, _ = ctx.process_host(frames[i], 1, out=out)
+            if lat is not None:
+                lat.append(time.perf_counter() - t0)
+            n += len(dets)
+        return n
+
+    # device-resident: one launch sequence (or graph replay) per frame, back to back, no host sync in between
+    ctx.set_frame_offset(0)
+    for _ in range(W):
+        for i in range(F):
+            ctx.process_device(dframes[i], 1)
+    env.sync_all()
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0.record(st)
+    for _ in range(K):
+        for i in range(F):
+            ctx.process_device(dframes[i], 1)
+    e1.record(st)
+    env.sync_all()
+    ms = env.max_over_ranks(e0.elapsed_time(e1))
+    fps = sensors_total * K / (ms * 1e-3)
+
+    # host path: every frame H2D -> chain -> D2H, synchronous per frame; wall-clock latency per call
+    for _ in range(W):
+        tick_host()
+    env.sync_all()
+    lat = []
+    t0 = time.perf_counter()
+    n_det = 0
+    for _ in range(K):
+        n_det = tick_host(lat)
+    t_e2e = env.max_over_ranks(time.perf_counter() - t0)
+    lat_us = np.sort(np.array(lat)) * 1e6
+    # the same tick as one batch (all sensors' frames together)
+    big = np.empty(F * ctx.max_det_per_frame, pkg.DET_DTYPE)
+    ctx.set_frame_offset(0)
+    for _ in range(2):
+        ctx.process_host(host, F, out=big)
+    t1 = time.perf_counter()
+    for _ in range(max(3, K)):
+        ctx.process_host(host, F, out=big)
+    tick_batched_ms = (time.perf_counter() - t1) / max(3, K) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_src = peaks()
+        b_alg = int(ctx.info.algorithmic_bytes_per_frame)
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"cfg5: {sensors_total} sensors x ({S} x {C} x {A}), one call per frame (latency mode), 2-D CA-CFAR, "
+                            f"{ctx.n_theta}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
+                "sensors_per_gpu": F, "sharding": f"sensor mod {world}", "cuda_graph": not args.no_graph,
+                "required_frames_per_s": 30 * sensors_total,
+                "latency_us": {"p50": float(lat_us[len(lat_us) // 2]), "p99": float(lat_us[min(len(lat_us) - 1, int(0.99 * len(lat_us)))]),
+                               "max": float(lat_us[-1]), "samples": int(len(lat_us)),
+                               "what": "wall clock of one mmw_process_host(1 frame) call: pinned host -> H2D -> 5 kernels -> D2H -> return"},
+                "tick_as_one_batch_ms": tick_batched_ms, "realtime_margin_x": (1000.0 / 30.0) / (t_e2e / K * 1e3),
+                "l2": "latency mode: one 1.5 MB frame per call (fits L2 by construction; this workload is launch/PCIe-latency bound, not HBM bound)",
+                "detections_last_tick": n_det,
+            },
+            "roofline": {"bound": "hbm", "kernel": "whole chain (latency-bound)", "achieved": b_alg * sensors_total * K / (ms * 1e-3) / 1e9 / world,
+                         "peak": peak, "unit": "GB/s", "frac": b_alg * sensors_total * K / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
+                         "note": "SURVEY.md 8d: cfg5 is latency-bound; the figure to read is config.latency_us"},
+            "e2e": {"value": sensors_total * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": F * ctx.frame_shorts * 2,
+                    "d2h_bytes_per_step": F * 32 + 24 * n_det, "steps": K, "api": "mmw_process_host, 1 frame per call"},
+            "gpu_launches": K * F * ctx.info.kernels_per_batch, "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            orc = entry.load_oracle()
+            orc.build()
+            cores = os.cpu_count() or 1
+            port = CpuPort(orc, pkg, S, C, A, cfg_idx + 1, cores)
+            n, dt, _ = port.run(port.passes_for(12.0))
+            line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": port.cores, "kind": "port",
+                                    "sample": f"{n} frames in {dt:.1f} s, plain-C fp64 oracle, {port.cores} OpenMP threads (frame-parallel)"}
+        env.emit(line)
+    ctx.close()
+
+
+def run_legacy(args, env):
+    """cfg1: the reference's own single-frame chain through the drop-in library"""
+    torch, pkg, dev, rank, world = env.torch, env.pkg, env.dev, env.rank, env.world
+    F = args.frames or WORKLOADS["cfg1"]["F"]
+    K, W = args.steps, args.warmup
+    orc = entry.load_oracle()
+    orc.build()
+    distinct = pkg.synth.legacy_capture(65, seed=rank)
+    base = orc.reshape(distinct[0], 100, 128, 4)[:12800]
+    reps = (F + 63) // 64
+    cap = np.tile(distinct[1:], (reps, 1))[:F]                      # F frames = 819 MB at F = 4096: larger than L2
+    frames = torch.from_numpy(cap).to(dev)
+    raw = torch.empty(F, dtype=torch.int32, device=dev)
+    L = pkg.api.load()
+    for _ in range(W):
+        pkg.api.legacy_process_device(frames, F, base, raw)
+    pkg.api.legacy_sync()
+    env.sync_all()
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    # device time: the library's own stream; wall clock around sync'd launches (kernel time >> launch latency at F = 4096)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        pkg.api.legacy_process_device(frames, F, base, raw)
+    pkg.api.legacy_sync()
+    ms = env.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    got = raw.cpu().numpy()
+    want = np.array([orc.legacy_frame(distinct[1 + f], base)[1] for f in range(8)])
+    assert np.array_equal(got[:8], want), "legacy raw bins differ from the reference CPU path"
+    fps = world * F * K / (ms * 1e-3)
+    # e2e (a): batched host entry point, pinned-free (the library stages); (b) the reference's calling pattern: one cudaProcessing per frame
+    n_host = min(F, 1024)
+    host = cap[:n_host]
+    pkg.api.legacy_process_frames(host, base)
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(K, 10))
+    for _ in range(e2e_steps):
+        pkg.api.legacy_process_frames(host, base)
+    t_e2e = env.max_over_ranks(time.perf_counter() - t0)
+    os.environ["MMW_LEGACY_QUIET"] = "1"
+    timers = np.zeros(4)
+    pkg.cudaProcessing(distinct[1], base, timers=timers)
+    t0 = time.perf_counter()
+    n_drop = 256
+    for f in range(n_drop):
+        pkg.cudaProcessing(distinct[1 + f % 64], base, timers=timers)
+    t_drop = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg = 51200                                                   # rx0 of one frame: 128 chirps x 100 samples x 4 B
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_text("cfg1"), "frames_per_gpu_per_step": F,
+                       "l2": f"inputs larger than L2: {F * 204800 / 1e6:.0f} MB of captures per step",
+                       "dropin_cudaProcessing_frames_per_s": n_drop / t_drop,
+                       "dropin_note": "the reference's own calling pattern: one synchronous cudaProcessing() per 200 KB frame (cudaBenchMarking.cpp:374-378)"},
+            "roofline": {"bound": "hbm", "kernel": "legacy_frame_kernel", "achieved": alg * F * K / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg * F * K / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg * F,
+                         "note": "one 16 384-point FFT per frame inside one SM's shared memory: shared-memory/issue bound, not HBM bound (only rx0, 1/4 of the capture, is read)"},
+            "e2e": {"value": world * n_host * e2e_steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": n_host * 204800,
+                    "d2h_bytes_per_step": n_host * 4, "steps": e2e_steps, "api": "mmw_legacy_process_frames"},
+            "gpu_launches": K, "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            port = LegacyCpu(orc, pkg)
+            n, dt = port.run(port.passes_for(10.0))
+            line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": port.kind,
+                                    "sample": f"{n} frames in {dt:.1f} s through the reference's cpuTiming() loop body "
+                                              f"({'compiled from /root/reference into oracle/_ref' if port.kind == 'reference' else 'oracle restatement'}), single thread like the reference"}
+        env.emit(line)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames (cfg5: sensors) per GPU per step (default: workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="cfg5: launch the kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--keep-cube", action="store_true", help="materialise the Doppler cube in HBM (default: fused)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    env = Env()
+    {"chain": run_chain, "stream": run_stream, "legacy": run_legacy}[WORKLOADS[args.workload]["kind"]](args, env)
+    env.finish()
 
 
 if __name__ == "__main__":

@@ -39,7 +39,9 @@ C_ABI_SYMBOLS = [
     "mmw_process_device", "mmw_process_host", "mmw_read_detections", "mmw_read_counts",
     "mmw_device_results", "mmw_device_result_block", "mmw_merge_gathered", "mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map",
     "mmw_copy_cfar_mask", "mmw_time_device",
+    "mmw_set_graph_mode", "mmw_set_base_frame", "mmw_process_capture_file", "mmw_default_radar_params", "mmw_to_physical",
     "mmw_legacy_process_frame", "mmw_legacy_process_frames", "mmw_legacy_copy_spectrum", "mmw_legacy_shutdown",
+    "mmw_legacy_process_device", "mmw_legacy_sync", "mmw_legacy_distance_from_raw", "mmw_legacy_process_file",
 ]
 # the reference's own entry point (acceleration.h:32), C++ linkage
 LEGACY_MANGLED = "_Z14cudaProcessingPsP9Complex_tiPdS2_S2_S2_"
@@ -60,6 +62,17 @@ class Info(C.Structure):
         ("adc_bytes_per_frame", C.c_longlong), ("algorithmic_bytes_per_frame", C.c_longlong),
         ("workspace_bytes", C.c_longlong), ("kernels_per_batch", C.c_int),
     ]
+
+
+class RadarParams(C.Structure):
+    """mmw_radar_params: the reference's radar constants (cudaBenchMarking.cpp:10-19)."""
+    _fields_ = [("f0_hz", C.c_double), ("slope_hz_per_s", C.c_double), ("fs_hz", C.c_double),
+                ("chirp_period_s", C.c_double), ("light_speed", C.c_double)]
+
+
+TARGET_DTYPE = np.dtype([("frame", "<u4"), ("range_m", "<f4"), ("velocity_mps", "<f4"), ("angle_deg", "<f4"),
+                         ("snr_db", "<f4"), ("flags", "<u4")])
+assert TARGET_DTYPE.itemsize == 24
 
 
 class RadarError(RuntimeError):
@@ -109,6 +122,16 @@ def load(build_if_missing: bool = True):
     for name in ("mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map", "mmw_copy_cfar_mask"):
         getattr(L, name).argtypes = [vp, C.c_int, vp]
     L.mmw_time_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.mmw_set_graph_mode.argtypes = [vp, C.c_int]
+    L.mmw_set_base_frame.argtypes = [vp, vp]
+    L.mmw_process_capture_file.argtypes = [vp, C.c_char_p, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, ip, ip]
+    L.mmw_default_radar_params.argtypes = [C.POINTER(RadarParams)]
+    L.mmw_default_radar_params.restype = None
+    L.mmw_to_physical.argtypes = [C.POINTER(RadarParams), C.c_int, C.c_int, vp, C.c_int, vp]
+    L.mmw_legacy_process_device.argtypes = [vp, C.c_int, vp, vp]
+    L.mmw_legacy_distance_from_raw.argtypes = [C.c_int]
+    L.mmw_legacy_distance_from_raw.restype = C.c_double
+    L.mmw_legacy_process_file.argtypes = [C.c_char_p, vp, vp, C.c_int, ip]
     L.mmw_legacy_process_frame.argtypes = [vp, vp, C.c_int, ip]
     L.mmw_legacy_process_frame.restype = C.c_double
     L.mmw_legacy_process_frames.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
@@ -210,6 +233,20 @@ class RadarContext:
         _check(self._L.mmw_get_windows(self._h, _np_ptr(wr), _np_ptr(wd)))
         return wr, wd
 
+    def set_base_frame(self, base_frame=None):
+        """Static-clutter removal: one frame in capture format subtracted from every frame (None turns it off)."""
+        if base_frame is None:
+            _check(self._L.mmw_set_base_frame(self._h, None))
+            return
+        b = np.ascontiguousarray(base_frame, np.int16).reshape(-1)
+        if b.size != self.frame_shorts:
+            raise ValueError("base frame must hold one frame (2*S*C*A int16)")
+        _check(self._L.mmw_set_base_frame(self._h, _np_ptr(b)))
+
+    def set_graph_mode(self, enable: bool):
+        """Replay the launch sequence of a batch as one CUDA graph (for one-frame-per-call streaming)."""
+        _check(self._L.mmw_set_graph_mode(self._h, int(bool(enable))))
+
     def set_frame_offset(self, first_frame: int):
         _check(self._L.mmw_set_frame_offset(self._h, int(first_frame)))
 
@@ -240,6 +277,18 @@ class RadarContext:
         n_det = C.c_int(0)
         rc = _check(self._L.mmw_process_host(self._h, C.c_void_p(ptr), n_frames, _np_ptr(dets), cap, C.byref(n_det)), True)
         return dets[: n_det.value], rc == MMW_ERR_OVERFLOW
+
+    def process_capture_file(self, path: str, first_frame: int = 0, max_frames: int = 0, use_first_as_base: bool = False,
+                             det_capacity: int = 1 << 20):
+        """Streams a raw capture file (the fhy_direct.bin format) through the chain. Returns (detections, frames done, overflow)."""
+        dets = np.empty(det_capacity, DET_DTYPE)
+        n_det, n_frames = C.c_int(0), C.c_int(0)
+        rc = _check(self._L.mmw_process_capture_file(self._h, os.fsencode(path), first_frame, max_frames, int(use_first_as_base),
+                                                     _np_ptr(dets), det_capacity, C.byref(n_det), C.byref(n_frames)), True)
+        return dets[: n_det.value].copy(), n_frames.value, rc == MMW_ERR_OVERFLOW
+
+    def to_physical(self, dets: np.ndarray, params: RadarParams | None = None) -> np.ndarray:
+        return to_physical(dets, self.Sp, self.Cp, params)
 
     def read_detections(self, det_capacity: int | None = None):
         cap = det_capacity if det_capacity is not None else self.max_frames * self.max_det_per_frame
@@ -300,6 +349,22 @@ class RadarContext:
         return (total.value, list(stages)) if per_stage else total.value
 
 
+def default_radar_params() -> RadarParams:
+    rp = RadarParams()
+    load().mmw_default_radar_params(C.byref(rp))
+    return rp
+
+
+def to_physical(dets: np.ndarray, Sp: int, Cp: int, params: RadarParams | None = None) -> np.ndarray:
+    """Detections -> range [m], radial velocity [m/s], angle [deg], SNR [dB] (mmw_to_physical; host arithmetic)."""
+    L = load()
+    params = params if params is not None else default_radar_params()
+    d = np.ascontiguousarray(dets, DET_DTYPE)
+    out = np.empty(d.size, TARGET_DTYPE)
+    _check(L.mmw_to_physical(C.byref(params), Sp, Cp, _np_ptr(d), d.size, _np_ptr(out)))
+    return out
+
+
 # ---------------------------------------------------------------------------
 # legacy entry point (reference cfg: 100 x 128 x 4)
 # ---------------------------------------------------------------------------
@@ -338,6 +403,30 @@ def legacy_process_frames(frames: np.ndarray, base_frame_rx0: np.ndarray):
     raw = np.empty(n, np.int32)
     _check(L.mmw_legacy_process_frames(_np_ptr(frames), n, _np_ptr(base), frames.shape[1], _np_ptr(dist), _np_ptr(raw)))
     return dist, raw
+
+
+def legacy_process_device(frames_dev, n_frames: int, base_frame_rx0: np.ndarray, raw_dev):
+    """Frames already in HBM -> raw arg-max bins in HBM (asynchronous; legacy_sync() waits)."""
+    base = np.ascontiguousarray(base_frame_rx0, np.complex128)
+    _check(load().mmw_legacy_process_device(C.c_void_p(_dev_ptr(frames_dev)), n_frames, _np_ptr(base), C.c_void_p(_dev_ptr(raw_dev))))
+
+
+def legacy_sync():
+    _check(load().mmw_legacy_sync())
+
+
+def legacy_distance_from_raw(raw: int) -> float:
+    return load().mmw_legacy_distance_from_raw(int(raw))
+
+
+def legacy_process_file(path: str, capacity: int = 4096):
+    """The reference's cudaTiming() loop in one call: frame 0 is the base frame, every later frame gives a distance."""
+    dist = np.empty(capacity, np.float64)
+    raw = np.empty(capacity, np.int32)
+    n = C.c_int(0)
+    _check(load().mmw_legacy_process_file(os.fsencode(path), _np_ptr(dist), _np_ptr(raw), capacity, C.byref(n)))
+    k = min(n.value, capacity)
+    return dist[:k].copy(), raw[:k].copy(), n.value
 
 
 def legacy_spectrum() -> np.ndarray:

@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "mmw_common.cuh"
@@ -50,6 +52,8 @@ struct mmw_ctx {
     float2 *d_tw_d, *d_tw_a, *d_tw1_r, *d_tw1_d;
     // workspace
     int16_t *d_adc;          // staging for host captures
+    int16_t *d_base;         // base frame for static-clutter removal (lazy)
+    int16_t *h_ring[2];      // pinned double buffer of the capture-file reader (lazy)
     float2 *d_rs;
     float2 *d_cube;
     float *d_pmap;
@@ -75,6 +79,11 @@ struct mmw_ctx {
     int last_frames;
     size_t workspace_bytes;
     cudaEvent_t ev[6];
+    // CUDA-graph mode (mmw_set_graph_mode): the launch sequence of one batch, captured once per distinct
+    // (capture address, frame count, frame offset, base frame, stream) and replayed with one cudaGraphLaunch
+    int graph_on;
+    int graph_warm;           // the first batch runs eagerly: launchers set function attributes on first use
+    std::map<std::tuple<const void *, int, uint32_t, const void *, void *>, cudaGraphExec_t> *graphs;
 };
 
 #define CK(call)                                                                                          \
@@ -154,11 +163,16 @@ void mmw_destroy(mmw_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
-    cudaFree(c->d_adc); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_mask);
+    cudaFree(c->d_adc); cudaFree(c->d_base); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_mask);
     cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_scratch);
     if (c->h_result) cudaFreeHost(c->h_result);
+    for (auto &h : c->h_ring) if (h) cudaFreeHost(h);
     for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->graphs) {
+        for (auto &kv : *c->graphs) cudaGraphExecDestroy(kv.second);
+        delete c->graphs;
+    }
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -260,6 +274,7 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     p.guard_r = Gr; p.guard_d = Gd; p.win_r_half = Gr + Tr; p.win_d_half = Gd + Td;
     p.alpha = cfg->cfar_alpha; p.lambda_over_d = cfg->lambda_over_d;
     p.max_det = cfg->max_det_per_frame; p.keep_cube = cfg->keep_doppler_cube ? 1 : 0; p.frame_offset = 0;
+    p.base_adc = nullptr;
     p.win_r = c->d_win_r; p.win_d = c->d_win_d; p.tw_d = c->d_tw_d; p.tw_a = c->d_tw_a; p.tw1_r = c->d_tw1_r; p.tw1_d = c->d_tw1_d;
 
     if ((rc = mmw_set_windows(c, nullptr, nullptr))) return fail(rc);
@@ -305,6 +320,29 @@ int mmw_set_frame_offset(mmw_ctx *c, uint32_t first_frame)
 {
     if (!c) { set_last_error("mmw_set_frame_offset: null context"); return MMW_ERR_ARG; }
     c->plan.frame_offset = first_frame;
+    return MMW_OK;
+}
+
+int mmw_set_base_frame(mmw_ctx *c, const int16_t *base_host)
+{
+    if (!c) { set_last_error("mmw_set_base_frame: null context"); return MMW_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (!base_host) { c->plan.base_adc = nullptr; return MMW_OK; }
+    const size_t frame_shorts = (size_t)2 * c->plan.S * c->plan.C * c->plan.A;
+    if (!c->d_base) {
+        int rc = dev_alloc(c, &c->d_base, frame_shorts);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpy(c->d_base, base_host, frame_shorts * sizeof(int16_t), cudaMemcpyHostToDevice));
+    c->plan.base_adc = c->d_base;
+    return MMW_OK;
+}
+
+int mmw_set_graph_mode(mmw_ctx *c, int enable)
+{
+    if (!c) { set_last_error("mmw_set_graph_mode: null context"); return MMW_ERR_ARG; }
+    c->graph_on = enable ? 1 : 0;
     return MMW_OK;
 }
 
@@ -357,6 +395,42 @@ static int run_batch(mmw_ctx *c, const int16_t *adc_dev, int n_frames, cudaEvent
     return run_back(c, n_frames, stage_ev);
 }
 
+// run_batch, or the replay of its captured graph when graph mode is on
+static int run_batch_graphed(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
+{
+    if (!c->graph_on) return run_batch(c, adc_dev, n_frames, nullptr);
+    if (!c->graph_warm) {
+        c->graph_warm = 1;
+        return run_batch(c, adc_dev, n_frames, nullptr);
+    }
+    if (!c->graphs) c->graphs = new std::map<std::tuple<const void *, int, uint32_t, const void *, void *>, cudaGraphExec_t>();
+    const auto key = std::make_tuple((const void *)adc_dev, n_frames, c->plan.frame_offset, (const void *)c->plan.base_adc, (void *)c->stream);
+    auto it = c->graphs->find(key);
+    if (it == c->graphs->end()) {
+        if (c->graphs->size() >= 256) {                       // bounded cache: start over rather than track recency
+            for (auto &kv : *c->graphs) cudaGraphExecDestroy(kv.second);
+            c->graphs->clear();
+        }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_batch(c, adc_dev, n_frames, nullptr);
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != MMW_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc == MMW_OK) set_last_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+            return rc != MMW_OK ? rc : MMW_ERR_CUDA;
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { set_last_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); return MMW_ERR_CUDA; }
+        it = c->graphs->emplace(key, exec).first;
+    }
+    CK(cudaGraphLaunch(it->second, c->stream));
+    c->last_frames = n_frames;
+    return MMW_OK;
+}
+
 static int check_batch_args(mmw_ctx *c, const void *adc, int n_frames, const char *who)
 {
     if (!c || !adc) { set_last_error("%s: null argument", who); return MMW_ERR_ARG; }
@@ -373,7 +447,7 @@ int mmw_process_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
     if (rc) return rc;
     if (((uintptr_t)adc_dev & 15u) != 0) { set_last_error("mmw_process_device: adc_dev must be 16-byte aligned"); return MMW_ERR_ARG; }
     CK(cudaSetDevice(c->device));
-    return run_batch(c, adc_dev, n_frames, nullptr);
+    return run_batch_graphed(c, adc_dev, n_frames);
 }
 
 // One D2H brings the header and the first `guess_det` records; a second copy is needed only when
@@ -403,22 +477,25 @@ static int fetch_results(mmw_ctx *c, mmw_detection *dets, int det_capacity, int 
     return rc;
 }
 
-int mmw_process_host(mmw_ctx *c, const int16_t *adc_host, int n_frames, mmw_detection *dets, int det_capacity, int *n_det)
+// Host capture -> device results, asynchronous.  The capture goes up in chunks on a copy stream; stages 1-3 of chunk k
+// run while chunk k+1 is still on the bus (frames are independent), stage 4 runs once over the whole batch.
+static int run_host_batch(mmw_ctx *c, const int16_t *adc_host, int n_frames)
 {
-    int rc = check_batch_args(c, adc_host, n_frames, "mmw_process_host");
-    if (rc) return rc;
-    CK(cudaSetDevice(c->device));
     const size_t frame_shorts = (size_t)2 * c->plan.S * c->plan.C * c->plan.A;
+    const size_t frame_bytes = frame_shorts * sizeof(int16_t);
+    int rc;
     if (!c->d_adc) {            // staging for host captures, allocated on first use
         rc = dev_alloc(c, &c->d_adc, (size_t)c->cfg.max_frames * frame_shorts);
         if (rc) return rc;
     }
-    // The capture goes up in chunks on a copy stream; stages 1-3 of chunk k run while chunk k+1 is still on
-    // the bus (frames are independent), stage 4 runs once over the whole batch.
-    const size_t frame_bytes = frame_shorts * sizeof(int16_t);
     int chunk = (int)((48u << 20) / frame_bytes);
     if (chunk < 1) chunk = 1;
     if (chunk * kMaxChunks < n_frames) chunk = (n_frames + kMaxChunks - 1) / kMaxChunks;
+    if (c->graph_on && n_frames <= chunk) {
+        // latency mode: one copy on the compute stream, then the whole launch sequence as one graph replay
+        CK(cudaMemcpyAsync(c->d_adc, adc_host, (size_t)n_frames * frame_bytes, cudaMemcpyHostToDevice, c->stream));
+        return run_batch_graphed(c, c->d_adc, n_frames);
+    }
     int k = 0;
     for (int first = 0; first < n_frames; first += chunk, ++k) {
         const int n = n_frames - first < chunk ? n_frames - first : chunk;
@@ -429,9 +506,134 @@ int mmw_process_host(mmw_ctx *c, const int16_t *adc_host, int n_frames, mmw_dete
         rc = run_front(c, c->d_adc, first, n, nullptr);
         if (rc) return rc;
     }
-    rc = run_back(c, n_frames, nullptr);
+    return run_back(c, n_frames, nullptr);
+}
+
+int mmw_process_host(mmw_ctx *c, const int16_t *adc_host, int n_frames, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    int rc = check_batch_args(c, adc_host, n_frames, "mmw_process_host");
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    rc = run_host_batch(c, adc_host, n_frames);
     if (rc) return rc;
     return fetch_results(c, dets, det_capacity, n_det);
+}
+
+// ---------------------------------------------------------------------------
+// capture-file ingest: fread into pinned double buffers, batch k+1 is read while batch k is on the GPU
+// ---------------------------------------------------------------------------
+int mmw_process_capture_file(mmw_ctx *c, const char *path, long long first_frame, int max_frames, int use_first_as_base,
+                             mmw_detection *dets, int det_capacity, int *n_det, int *n_frames_done)
+{
+    if (n_det) *n_det = 0;
+    if (n_frames_done) *n_frames_done = 0;
+    if (!c || !path) { set_last_error("mmw_process_capture_file: null argument"); return MMW_ERR_ARG; }
+    if (first_frame < 0 || det_capacity < 0 || (det_capacity > 0 && !dets)) { set_last_error("mmw_process_capture_file: bad argument"); return MMW_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    const size_t frame_shorts = (size_t)2 * c->plan.S * c->plan.C * c->plan.A;
+    const size_t frame_bytes = frame_shorts * sizeof(int16_t);
+    const int B = c->cfg.max_frames;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) { set_last_error("unable to read the specified file: %s", path); return MMW_ERR_ARG; }    // the reference's message, cudaBenchMarking.cpp:346
+    if (first_frame > 0 && fseeko(fp, (off_t)(first_frame * (long long)frame_bytes), SEEK_SET) != 0) {
+        fclose(fp);
+        set_last_error("mmw_process_capture_file: cannot seek to frame %lld", first_frame);
+        return MMW_ERR_ARG;
+    }
+    for (auto &h : c->h_ring)
+        if (!h && cudaMallocHost((void **)&h, (size_t)B * frame_bytes) != cudaSuccess) {
+            fclose(fp);
+            set_last_error("cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MMW_ERR_CUDA;
+        }
+    // reads up to `want` frames into `dst`; a trailing partial frame is zero-filled and counted
+    auto read_frames = [&](int16_t *dst, int want) -> int {
+        if (want <= 0) return 0;
+        const size_t got = fread(dst, sizeof(int16_t), (size_t)want * frame_shorts, fp);
+        const size_t whole = got / frame_shorts, rest = got % frame_shorts;
+        if (rest) {
+            memset(dst + got, 0, (frame_shorts - rest) * sizeof(int16_t));
+            return (int)whole + 1;
+        }
+        return (int)whole;
+    };
+    const uint32_t saved_offset = c->plan.frame_offset;
+    long long frame_no = first_frame;           // file index of the next frame to be read
+    long long budget = max_frames > 0 ? (long long)max_frames : -1;
+    int rc = MMW_OK, total_det = 0, total_frames = 0, overflow = 0;
+    if (use_first_as_base) {
+        if (read_frames(c->h_ring[0], 1) == 1) {
+            rc = mmw_set_base_frame(c, c->h_ring[0]);
+            ++frame_no;
+        }
+    }
+    int cur = 0;
+    int n_cur = rc ? 0 : read_frames(c->h_ring[0 + cur], (int)(budget < 0 || budget > B ? B : budget));
+    while (rc == MMW_OK && n_cur > 0) {
+        if (budget > 0) budget -= n_cur;
+        // queue batch `cur` (H2D chunks + kernels are asynchronous until fetch_results), then read the next batch
+        // from the file while the GPU works
+        c->plan.frame_offset = (uint32_t)frame_no;
+        rc = run_host_batch(c, c->h_ring[cur], n_cur);
+        const int want_next = budget == 0 ? 0 : (int)(budget < 0 || budget > B ? B : budget);
+        const int n_next = rc == MMW_OK ? read_frames(c->h_ring[cur ^ 1], want_next) : 0;      // overlaps the GPU work above
+        if (rc == MMW_OK) {
+            int got = 0;
+            rc = fetch_results(c, dets ? dets + total_det : nullptr, det_capacity - total_det, &got);
+            if (rc == MMW_ERR_OVERFLOW) { overflow = 1; rc = MMW_OK; }
+            total_det += got;
+            total_frames += n_cur;
+            frame_no += n_cur;
+        }
+        cur ^= 1;
+        n_cur = n_next;
+    }
+    fclose(fp);
+    c->plan.frame_offset = saved_offset;
+    if (n_det) *n_det = total_det;
+    if (n_frames_done) *n_frames_done = total_frames;
+    if (rc == MMW_OK && overflow) {
+        set_last_error("detection list truncated while reading %s", path);
+        return MMW_ERR_OVERFLOW;
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// detections -> physical units (host arithmetic, mirrors cudaBenchMarking.cpp:10-19 and :301-303)
+// ---------------------------------------------------------------------------
+void mmw_default_radar_params(mmw_radar_params *rp)
+{
+    if (!rp) return;
+    rp->f0_hz = 77e9;
+    rp->slope_hz_per_s = 5.987e12;
+    rp->fs_hz = 2.0e6;
+    rp->chirp_period_s = 64e-6;
+    rp->light_speed = 3.0e8;
+}
+
+int mmw_to_physical(const mmw_radar_params *rp, int Sp, int Cp, const mmw_detection *dets, int n, mmw_target *out)
+{
+    if (!rp || Sp < 1 || Cp < 1 || n < 0 || (n > 0 && (!dets || !out))) { set_last_error("mmw_to_physical: bad argument"); return MMW_ERR_ARG; }
+    if (rp->f0_hz <= 0 || rp->slope_hz_per_s <= 0 || rp->fs_hz <= 0 || rp->chirp_period_s <= 0 || rp->light_speed <= 0) {
+        set_last_error("mmw_to_physical: radar parameters must be positive");
+        return MMW_ERR_ARG;
+    }
+    const double lambda = rp->light_speed / rp->f0_hz;
+    for (int i = 0; i < n; ++i) {
+        const mmw_detection &d = dets[i];
+        const double f_beat = (double)d.range_bin / (double)Sp * rp->fs_hz;
+        const int dw = d.doppler_bin < Cp / 2 ? (int)d.doppler_bin : (int)d.doppler_bin - Cp;
+        const double f_dop = (double)dw / ((double)Cp * rp->chirp_period_s);
+        mmw_target &t = out[i];
+        t.frame = d.frame;
+        t.range_m = (float)(rp->light_speed * f_beat / (2.0 * rp->slope_hz_per_s));
+        t.velocity_mps = (float)(0.5 * lambda * f_dop);
+        t.angle_deg = (float)((double)d.angle_rad * (180.0 / M_PI));
+        t.snr_db = (d.noise > 0.f && d.power > 0.f) ? (float)(10.0 * log10((double)d.power / (double)d.noise)) : 0.f;
+        t.flags = d.flags;
+    }
+    return MMW_OK;
 }
 
 int mmw_read_detections(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)

@@ -26,6 +26,7 @@ struct PlanDev {
     const float2 *tw1_r;    // [Sp]  pass-1 twiddles of the range FFT in consumption order (tw1_index)
     const float2 *tw1_d;    // [Cp]  pass-1 twiddles of the Doppler FFT in consumption order
     const float2 *tw_a;     // [n_theta]
+    const int16_t *base_adc; // one frame [C][A][S] IIQQ subtracted before the range window, or nullptr (static-clutter removal)
 };
 
 // internal HBM layouts

@@ -412,6 +412,96 @@ int mmw_legacy_process_frames(const short *frames_host, int n_frames, const doub
     return MMW_OK;
 }
 
+int mmw_legacy_process_device(const short *frames_dev, int n_frames, const double *base_frame_host, int *raw_dev)
+{
+    if (!frames_dev || !base_frame_host || n_frames <= 0 || !raw_dev) {
+        mmw::set_last_error("mmw_legacy_process_device: bad argument");
+        return MMW_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init() != cudaSuccess || upload_base(base_frame_host) != cudaSuccess) return MMW_ERR_CUDA;
+    LegacyArgs a;
+    a.frames = frames_dev;
+    a.base = g.d_base;
+    a.tw = g.d_tw;
+    a.spectrum = nullptr;
+    a.raw = raw_dev;
+    a.size = kFrameShorts;
+    legacy_frame_kernel<<<n_frames, kNT, kSmemBytes, g.stream>>>(a);
+    if (cudaGetLastError() != cudaSuccess) {
+        mmw::set_last_error("legacy_frame_kernel launch failed");
+        return MMW_ERR_CUDA;
+    }
+    return MMW_OK;
+}
+
+int mmw_legacy_sync(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.ready) return MMW_OK;
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess) {
+        mmw::set_last_error("mmw_legacy_sync: %s", cudaGetErrorString(cudaGetLastError()));
+        return MMW_ERR_CUDA;
+    }
+    return MMW_OK;
+}
+
+double mmw_legacy_distance_from_raw(int raw_index) { return distance_from_raw(raw_index); }
+
+// The reference's cudaTiming() (cudaBenchMarking.cpp:334-395) in one call.
+int mmw_legacy_process_file(const char *path, double *distances, int *raw_indices, int capacity, int *n_frames)
+{
+    if (n_frames) *n_frames = 0;
+    if (!path || capacity < 0 || (capacity > 0 && !distances)) {
+        mmw::set_last_error("mmw_legacy_process_file: bad argument");
+        return MMW_ERR_ARG;
+    }
+    FILE *fp = fopen(path, "rb");
+    if (!fp) {
+        mmw::set_last_error("unable to read the specified file: %s", path);     // the reference's message (:346)
+        return MMW_ERR_ARG;
+    }
+    constexpr int kBatch = 256;
+    short *buf = (short *)malloc((size_t)kBatch * kFrameShorts * sizeof(short));
+    double *base = (double *)malloc((size_t)kValid * 2 * sizeof(double));
+    int rc = MMW_OK, done = 0;
+    // frame 0 -> base frame, rx0 only, [chirp][sample] (ReshapeComplex_t + memmove, cudaBenchMarking.cpp:357-365)
+    size_t got = fread(buf, sizeof(short), kFrameShorts, fp);
+    if (got == 0) rc = MMW_ERR_ARG, mmw::set_last_error("mmw_legacy_process_file: empty capture %s", path);
+    if (rc == MMW_OK) {
+        for (int n = 0; n < kValid; ++n) {
+            const int c = n / kS, sidx = n - c * kS;
+            const int e = c * (kA * kS) + sidx;
+            const size_t gidx = (size_t)4 * (e >> 1) + (e & 1);
+            base[2 * n] = gidx + 2 < got ? (double)buf[gidx] : 0.0;
+            base[2 * n + 1] = gidx + 2 < got ? (double)buf[gidx + 2] : 0.0;
+        }
+        std::lock_guard<std::mutex> lk(g_mu);
+        while (rc == MMW_OK && (got = fread(buf, sizeof(short), (size_t)kBatch * kFrameShorts, fp)) > 0) {
+            const int whole = (int)(got / kFrameShorts), rest = (int)(got % kFrameShorts);
+            if (whole > 0 && run_frames(buf, whole, base, kFrameShorts, false) != cudaSuccess) { rc = MMW_ERR_CUDA; break; }
+            for (int f = 0; f < whole; ++f, ++done)
+                if (done < capacity) {
+                    distances[done] = distance_from_raw(g.h_raw[f]);
+                    if (raw_indices) raw_indices[done] = g.h_raw[f];
+                }
+            if (rest) {       // short final read: the reference hands the short count on and processes the frame (:374-377)
+                if (run_frames(buf + (size_t)whole * kFrameShorts, 1, base, rest, false) != cudaSuccess) { rc = MMW_ERR_CUDA; break; }
+                if (done < capacity) {
+                    distances[done] = distance_from_raw(g.h_raw[0]);
+                    if (raw_indices) raw_indices[done] = g.h_raw[0];
+                }
+                ++done;
+            }
+        }
+    }
+    free(buf);
+    free(base);
+    fclose(fp);
+    if (n_frames) *n_frames = done;
+    return rc;
+}
+
 int mmw_legacy_copy_spectrum(float *out)
 {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -58,7 +58,10 @@ struct RangeSmem {
 // PAIR: a thread runs butterflies n2 and n2+1 together (one 8-byte load yields both samples of an IIQQ group).
 // PAD : n_samples < N (zero padding needs a bound check per load); CT: compile-time n_chirps, 0 = run time.
 // NSTAGE = 1: one staging buffer, refilled behind pass 2; NSTAGE = 2: double buffer, refilled a whole tile ahead.
-template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE>
+// BASE: static-clutter removal — p.base_adc (one frame in capture format) is subtracted sample by sample, in integers,
+// before the window (the reference's base-frame subtraction, acceleration.cu:152-166, for every antenna).  The base frame
+// is a few MB read by every CTA, so it is served from L2 with plain read-only loads rather than staged.
+template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE>
 __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
                                                             int n_tiles)
 {
@@ -123,6 +126,9 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
         if (NSTAGE == 2 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
         mbar_wait(&bar[it % NSTAGE], (uint32_t)((it / NSTAGE) & 1));
         const unsigned char *srow = stage + (it % NSTAGE) * L::kStageBytes + row * L::kStageStride;
+        const unsigned char *brow = nullptr;
+        if constexpr (BASE)
+            brow = reinterpret_cast<const unsigned char *>(p.base_adc) + ((size_t)min(c0 + row, C - 1) * A + (fa % A)) * (size_t)(4 * S);
 
         // ---- pass 1: R2 butterflies of radix R1 over stride R2, reading the staged int16 rows ----
         if constexpr (PAIR) {
@@ -136,8 +142,14 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
                     if (!PAD || n < S) {
                         const uint2 raw = *reinterpret_cast<const uint2 *>(srow + 4 * n);   // [I(n) I(n+1)] [Q(n) Q(n+1)]
                         const float2 w = *reinterpret_cast<const float2 *>(win + n);
-                        xa[m] = make_float2((float)(short)(raw.x & 0xffffu) * w.x, (float)(short)(raw.y & 0xffffu) * w.x);
-                        xb[m] = make_float2((float)((int)raw.x >> 16) * w.y, (float)((int)raw.y >> 16) * w.y);
+                        int i0 = (short)(raw.x & 0xffffu), q0 = (short)(raw.y & 0xffffu), i1 = (int)raw.x >> 16, q1 = (int)raw.y >> 16;
+                        if constexpr (BASE) {
+                            const uint2 rb = __ldg(reinterpret_cast<const uint2 *>(brow + 4 * n));
+                            i0 -= (short)(rb.x & 0xffffu); q0 -= (short)(rb.y & 0xffffu);
+                            i1 -= (int)rb.x >> 16;         q1 -= (int)rb.y >> 16;
+                        }
+                        xa[m] = make_float2((float)i0 * w.x, (float)q0 * w.x);
+                        xb[m] = make_float2((float)i1 * w.y, (float)q1 * w.y);
                     } else {
                         xa[m] = xb[m] = make_float2(0.f, 0.f);
                     }
@@ -170,8 +182,13 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
                     if (!PAD || n < S) {
                         const uint2 raw = *reinterpret_cast<const uint2 *>(srow + 4 * (n - odd));
                         const float w = win[n];
-                        const int iv = odd ? ((int)raw.x >> 16) : (int)(short)(raw.x & 0xffffu);
-                        const int qv = odd ? ((int)raw.y >> 16) : (int)(short)(raw.y & 0xffffu);
+                        int iv = odd ? ((int)raw.x >> 16) : (int)(short)(raw.x & 0xffffu);
+                        int qv = odd ? ((int)raw.y >> 16) : (int)(short)(raw.y & 0xffffu);
+                        if constexpr (BASE) {
+                            const uint2 rb = __ldg(reinterpret_cast<const uint2 *>(brow + 4 * (n - odd)));
+                            iv -= odd ? ((int)rb.x >> 16) : (int)(short)(rb.x & 0xffffu);
+                            qv -= odd ? ((int)rb.y >> 16) : (int)(short)(rb.y & 0xffffu);
+                        }
                         x[m] = make_float2((float)iv * w, (float)qv * w);
                     } else {
                         x[m] = make_float2(0.f, 0.f);
@@ -218,25 +235,41 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
 // ---------------------------------------------------------------------------
 // K2: Doppler FFT + non-coherent integration
 // ---------------------------------------------------------------------------
-template <int N, int BT, int NSTAGE>
+// INPLACE: pass 1 writes its outputs back into the staging row it read (a thread reads and writes the same R1
+// addresses, so there is no hazard), which frees the separate work buffer: the same footprint then holds three
+// staging buffers instead of two, i.e. two loads in flight per CTA while a third is being transformed.
+template <int N, int BT, int NSTAGE, bool INPLACE = false>
 struct DopplerSmem {
-    static constexpr int kStageRow = N + 2;                          // float2 per staged row (16-byte multiple)
-    static constexpr int kOffTw = 16;
+    static constexpr int kStageRow = N + 2;                          // float2 per staged row (16-byte multiple; conflict-free
+                                                                     // for 16 rows x 2 sub-slots of 8-byte accesses)
+    static constexpr int kOffTw = 32;                                // up to four mbarriers in front
     static constexpr int kOffStage = kOffTw + 8 * N;
     static constexpr int kStageBytes = BT * kStageRow * 8;
     static constexpr int kOffWork = kOffStage + NSTAGE * kStageBytes;
-    static constexpr int kBytes = kOffWork + BT * (N + 1) * 8;
+    static constexpr int kBytes = kOffWork + (INPLACE ? 0 : BT * (N + 1) * 8);
+    static constexpr int kWorkRow = INPLACE ? kStageRow : N + 1;
 };
 
 // PAD: n_chirps < N.  SPT: compile-time Sp (range FFT length = stride of the power map / cube), 0 = run time.
 // NSTAGE = 2: the next step is prefetched while the current one is transformed (double buffer);
 // NSTAGE = 1: one staging buffer, refilled behind pass 2 (smaller footprint -> more CTAs per SM).
-template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE>
-__global__ void __launch_bounds__(NW * 32, (2 * DopplerSmem<N, BT, NSTAGE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) doppler_fft_kernel(PlanDev p, const float2 *__restrict__ rs, float2 *__restrict__ cube,
+template <int N, int BT, int NW, int NSTAGE, bool INPLACE>
+constexpr int doppler_min_ctas()
+{
+    constexpr int by_smem = (226 * 1024) / DopplerSmem<N, BT, NSTAGE, INPLACE>::kBytes;
+    constexpr int by_threads = 768 / (NW * 32);                      // keeps >= 85 registers per thread
+    constexpr int m = by_smem < by_threads ? by_smem : by_threads;
+    return m < 1 ? 1 : (m > 3 ? 3 : m);
+}
+
+template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE, bool INPLACE>
+__global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, INPLACE>()) doppler_fft_kernel(PlanDev p, const float2 *__restrict__ rs, float2 *__restrict__ cube,
                                                                float *__restrict__ pmap, int n_tiles)
 {
     static_assert(R1 * R2 == N, "plan");
-    using L = DopplerSmem<N, BT, NSTAGE>;
+    static_assert(NSTAGE >= 1 && NSTAGE <= 4, "stages");
+    static_assert(!INPLACE || NSTAGE >= 2, "in-place needs a second buffer to prefetch into");
+    using L = DopplerSmem<N, BT, NSTAGE, INPLACE>;
     constexpr int NT = NW * 32;
     constexpr int SUBS = 32 / BT;
     constexpr int NSLOT = NW * SUBS;
@@ -247,10 +280,10 @@ __global__ void __launch_bounds__(NW * 32, (2 * DopplerSmem<N, BT, NSTAGE>::kByt
     constexpr bool TWREG = UPS1 * (R1 - 1) <= 16;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);              // two barriers
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);              // NSTAGE barriers
     float2 *tw = reinterpret_cast<float2 *>(smem + L::kOffTw);
     float2 *stage = reinterpret_cast<float2 *>(smem + L::kOffStage);
-    float2 *work = reinterpret_cast<float2 *>(smem + L::kOffWork);
+    float2 *work = reinterpret_cast<float2 *>(smem + L::kOffWork);      // unused when INPLACE
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = lane % BT, sub = lane / BT, slot = warp * SUBS + sub;
@@ -258,10 +291,15 @@ __global__ void __launch_bounds__(NW * 32, (2 * DopplerSmem<N, BT, NSTAGE>::kByt
     const int Sp = SPT ? SPT : p.Sp;
     const int nrt = Sp / BT;
 
-    // a "step" is one antenna of one tile; steps of consecutive tiles are pipelined back to back
-    auto issue = [&](int tile, int a, int s) {
+    // a "step" is one antenna of one tile; the q-th step of this CTA is antenna q % A of its (q / A)-th tile, and
+    // steps of consecutive tiles are pipelined back to back
+    auto issue_step = [&](int q) {                                    // warp 0
+        const int itq = q / A, a = q - itq * A;
+        const long long tl = (long long)blockIdx.x + (long long)itq * gridDim.x;
+        if (tl >= n_tiles) return;
+        const int tile = (int)tl;
         const int rt = tile % nrt, f = tile / nrt;
-        const int buf = s % NSTAGE;
+        const int buf = q % NSTAGE;
         uint64_t *b = &bar[buf];
         if (lane == 0) {
             fence_proxy_async();
@@ -273,23 +311,23 @@ __global__ void __launch_bounds__(NW * 32, (2 * DopplerSmem<N, BT, NSTAGE>::kByt
             bulk_g2s(stage + (size_t)buf * (BT * L::kStageRow) + lane * L::kStageRow, src, (uint32_t)(C * 8), b);
         }
     };
-    auto prefetch_next = [&](int tile, int a, int s) {                // the step after (tile, a), possibly of the next tile
-        if (a + 1 < A) issue(tile, a + 1, s + 1);
-        else if (tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, 0, s + 1);
-    };
+    // how far ahead of the step being transformed the loads run
+    constexpr int AHEAD = INPLACE ? NSTAGE - 1 : 1;
 
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+#pragma unroll
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(&bar[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
     int tile = blockIdx.x;
-    if (warp == 0 && tile < n_tiles) issue(tile, 0, 0);
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < AHEAD; ++i) issue_step(i);
+    }
     for (int i = tid; i < N; i += NT) tw[i] = p.tw1_d[i];
     __syncthreads();
 
-    float2 *wrow = work + row * (N + 1);
     int s = 0;                                                        // running step counter of this CTA
     float2 twr[TWREG ? UPS1 : 1][TWREG ? R1 - 1 : 1];
     if constexpr (TWREG) {
@@ -311,9 +349,12 @@ __global__ void __launch_bounds__(NW * 32, (2 * DopplerSmem<N, BT, NSTAGE>::kByt
 
 #pragma unroll 1
         for (int a = 0; a < A; ++a, ++s) {
-            if (NSTAGE == 2 && warp == 0) prefetch_next(tile, a, s);
+            // the buffer step s + AHEAD lands in was released by the barrier that ended step s - 1 (in-place) /
+            // is the other half of the double buffer
+            if ((INPLACE || NSTAGE == 2) && warp == 0) issue_step(s + AHEAD);
             mbar_wait(&bar[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
-            const float2 *srow = stage + (size_t)(s % NSTAGE) * (BT * L::kStageRow) + row * L::kStageRow;
+            float2 *srow = stage + (size_t)(s % NSTAGE) * (BT * L::kStageRow) + row * L::kStageRow;
+            float2 *wrow = INPLACE ? srow : work + row * (N + 1);
 
             // pass 1: R2 butterflies of radix R1 over stride R2 (Doppler window already applied by K1)
 #pragma unroll
@@ -337,7 +378,7 @@ __global__ void __launch_bounds__(NW * 32, (2 * DopplerSmem<N, BT, NSTAGE>::kByt
                 }
             }
             __syncthreads();
-            if (NSTAGE == 1 && warp == 0) prefetch_next(tile, a, s);   // staging buffer consumed: refill behind pass 2
+            if (!INPLACE && NSTAGE == 1 && warp == 0) issue_step(s + 1);   // staging buffer consumed: refill behind pass 2
 
             // pass 2: radix R2 on contiguous runs; accumulate |X|^2 (ascending antenna order)
 #pragma unroll
@@ -430,10 +471,10 @@ static cudaError_t resident_ctas(K kernel, int threads, int smem_bytes, int *cta
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, threads, smem_bytes);
 }
 
-template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE>
+template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE = false>
 static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
-    auto k = range_fft_kernel<N, R1, R2, BT, NW, PAIR, PAD, CT, NSTAGE>;
+    auto k = range_fft_kernel<N, R1, R2, BT, NW, PAIR, PAD, CT, NSTAGE, BASE>;
     constexpr int bytes = RangeSmem<N, BT, NSTAGE>::kBytes;
     static int per_sm = 0;
     if (!per_sm) {
@@ -452,6 +493,10 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, int CT0, int CT1, int NSTAGE = 1>
 static cudaError_t run_range(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
+    if (p.base_adc != nullptr) {          // static-clutter removal: one generic instantiation per padding mode
+        if (p.S == N) return run_range_t<N, R1, R2, BT, NW, PAIR, false, 0, NSTAGE, true>(p, adc, rs, n_frames, st);
+        return run_range_t<N, R1, R2, BT, NW, PAIR, true, 0, NSTAGE, true>(p, adc, rs, n_frames, st);
+    }
     if (p.S == N) {
         if (CT0 && p.C == CT0) return run_range_t<N, R1, R2, BT, NW, PAIR, false, CT0, NSTAGE>(p, adc, rs, n_frames, st);
         if (CT1 && p.C == CT1) return run_range_t<N, R1, R2, BT, NW, PAIR, false, CT1, NSTAGE>(p, adc, rs, n_frames, st);
@@ -462,11 +507,11 @@ static cudaError_t run_range(const PlanDev &p, const int16_t *adc, float2 *rs, i
 
 static int variant(const char *name);
 
-template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE>
+template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE, bool INPLACE>
 static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
-    auto k = doppler_fft_kernel<N, R1, R2, BT, NW, PAD, SPT, NSTAGE>;
-    constexpr int bytes = DopplerSmem<N, BT, NSTAGE>::kBytes;
+    auto k = doppler_fft_kernel<N, R1, R2, BT, NW, PAD, SPT, NSTAGE, INPLACE>;
+    constexpr int bytes = DopplerSmem<N, BT, NSTAGE, INPLACE>::kBytes;
     static int per_sm = 0;
     if (!per_sm) {
         cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
@@ -479,15 +524,15 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
     return cudaGetLastError();
 }
 
-template <int N, int R1, int R2, int BT, int NW, int SP0, int SP1, int NSTAGE = 2>
+template <int N, int R1, int R2, int BT, int NW, int SP0, int SP1, int NSTAGE = 2, bool INPLACE = false>
 static cudaError_t run_doppler(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
     if (p.C == N) {
-        if (SP0 && p.Sp == SP0) return run_doppler_t<N, R1, R2, BT, NW, false, SP0, NSTAGE>(p, rs, cube, pmap, n_frames, st);
-        if (SP1 && p.Sp == SP1) return run_doppler_t<N, R1, R2, BT, NW, false, SP1, NSTAGE>(p, rs, cube, pmap, n_frames, st);
-        return run_doppler_t<N, R1, R2, BT, NW, false, 0, NSTAGE>(p, rs, cube, pmap, n_frames, st);
+        if (SP0 && p.Sp == SP0) return run_doppler_t<N, R1, R2, BT, NW, false, SP0, NSTAGE, INPLACE>(p, rs, cube, pmap, n_frames, st);
+        if (SP1 && p.Sp == SP1) return run_doppler_t<N, R1, R2, BT, NW, false, SP1, NSTAGE, INPLACE>(p, rs, cube, pmap, n_frames, st);
+        return run_doppler_t<N, R1, R2, BT, NW, false, 0, NSTAGE, INPLACE>(p, rs, cube, pmap, n_frames, st);
     }
-    return run_doppler_t<N, R1, R2, BT, NW, true, 0, NSTAGE>(p, rs, cube, pmap, n_frames, st);
+    return run_doppler_t<N, R1, R2, BT, NW, true, 0, NSTAGE, INPLACE>(p, rs, cube, pmap, n_frames, st);
 }
 
 static int variant(const char *name)
@@ -512,20 +557,10 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     switch (p.Sp) {
     case 64:   return run_range<64, 8, 8, 16, 4, true, 0, 0>(p, adc, rs, n_frames, st);
     case 128:  return run_range<128, 8, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
-    case 256: {
-        const int v = variant("MMW_K1_VARIANT");
-        if (v == 1) return run_range<256, 16, 16, 8, 4, true, 128, 0, 2>(p, adc, rs, n_frames, st);
-        if (v == 2) return run_range<256, 16, 16, 16, 4, true, 128, 0, 2>(p, adc, rs, n_frames, st);
-        if (v == 3) return run_range<256, 16, 16, 8, 4, true, 128, 0, 1>(p, adc, rs, n_frames, st);
-        return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
-    }
-    case 512: {
-        const int v = variant("MMW_K1_VARIANT");
-        if (v == 1) return run_range<512, 16, 32, 8, 4, true, 256, 0, 2>(p, adc, rs, n_frames, st);
-        if (v == 2) return run_range<512, 16, 32, 16, 8, true, 256, 0, 2>(p, adc, rs, n_frames, st);
-        if (v == 3) return run_range<512, 16, 32, 8, 4, true, 256, 0, 1>(p, adc, rs, n_frames, st);
-        return run_range<512, 16, 32, 16, 8, true, 256, 0>(p, adc, rs, n_frames, st);
-    }
+    // double-buffered staging (NSTAGE = 2) and BT = 8 tiles were measured slower for 256 and 512 points
+    // (profiles/experiments/r1_k1_variants_sweep.log); the single-buffer BT = 16 shape stays
+    case 256:  return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
+    case 512:  return run_range<512, 16, 32, 16, 8, true, 256, 0>(p, adc, rs, n_frames, st);
     case 1024: return run_range<1024, 32, 32, 16, 8, false, 512, 0>(p, adc, rs, n_frames, st);
     default:   return cudaErrorInvalidValue;
     }
@@ -542,6 +577,10 @@ cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube,
         if (v == 3) return run_doppler<128, 8, 16, 8, 4, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
         if (v == 4) return run_doppler<128, 8, 16, 16, 8, 256, 128, 2>(p, rs, cube, pmap, n_frames, st);
         if (v == 5) return run_doppler<128, 8, 16, 32, 8, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
+        if (v == 6) return run_doppler<128, 8, 16, 16, 4, 256, 128, 3, true>(p, rs, cube, pmap, n_frames, st);
+        if (v == 7) return run_doppler<128, 8, 16, 16, 4, 256, 128, 4, true>(p, rs, cube, pmap, n_frames, st);
+        if (v == 8) return run_doppler<128, 8, 16, 16, 4, 256, 128, 2, true>(p, rs, cube, pmap, n_frames, st);
+        if (v == 9) return run_doppler<128, 8, 16, 16, 8, 256, 128, 3, true>(p, rs, cube, pmap, n_frames, st);
         return run_doppler<128, 8, 16, 16, 4, 256, 128>(p, rs, cube, pmap, n_frames, st);
     }
     case 256: {
@@ -551,6 +590,10 @@ cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube,
         if (v == 3) return run_doppler<256, 16, 16, 8, 4, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
         if (v == 4) return run_doppler<256, 16, 16, 16, 4, 512, 0, 2>(p, rs, cube, pmap, n_frames, st);
         if (v == 5) return run_doppler<256, 16, 16, 16, 4, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
+        if (v == 6) return run_doppler<256, 16, 16, 16, 8, 512, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
+        if (v == 7) return run_doppler<256, 16, 16, 16, 8, 512, 0, 2, true>(p, rs, cube, pmap, n_frames, st);
+        if (v == 8) return run_doppler<256, 16, 16, 16, 4, 512, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
+        if (v == 9) return run_doppler<256, 16, 16, 16, 8, 512, 0, 4, true>(p, rs, cube, pmap, n_frames, st);
         return run_doppler<256, 16, 16, 16, 8, 512, 0>(p, rs, cube, pmap, n_frames, st);
     }
     case 512:  return run_doppler<512, 16, 32, 16, 8, 1024, 0>(p, rs, cube, pmap, n_frames, st);

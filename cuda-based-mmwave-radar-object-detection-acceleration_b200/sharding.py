@@ -75,7 +75,7 @@ def gather_detections(local_records, n_local, group=None):
 
 
 class DetectionGather:
-    """The exchange step of the sharded chain without a host round trip.
+    """The exchange step of the sharded chain without a host round trip, pipelined one step behind the compute.
 
     Every rank contributes a FIXED-size prefix of its contiguous result block ([32-byte header | ordered
     records], mmw_device_result_block) — `records_per_rank` records, a few hundred KB — so the sizes NCCL needs
@@ -83,7 +83,11 @@ class DetectionGather:
     with one gather over NVLink and packs them into one ordered list with one launch of the library's merge
     kernel (mmw_merge_gathered), reading the true counts from the gathered headers on the device.  A rank that
     produced more than `records_per_rank` detections is truncated and the merged header's overflow word is set.
-    Everything is asynchronous on the context's stream (which must be torch's current stream)."""
+
+    Pipelining: run() snapshots the result block (one small device copy on the compute stream), starts the
+    gather asynchronously (NCCL's own stream) and only then completes the PREVIOUS step's exchange (wait + merge),
+    so the transfer of step k overlaps the kernels of step k+1 instead of stalling the compute stream.
+    flush() completes the last one.  The context's stream must be torch's current stream."""
 
     def __init__(self, ctx, device, records_per_rank: int, group=None):
         import torch
@@ -96,26 +100,51 @@ class DetectionGather:
         if self.stride > cap_bytes:
             raise ValueError("records_per_rank exceeds the context's detection capacity")
         self.local = device_bytes_view(block, self.stride, device)
+        self.send = [torch.empty(self.stride, dtype=torch.uint8, device=device) for _ in range(2)]
         self.merged_cap = self.world * records_per_rank
+        self.work = [None, None]
+        self.step = 0
+        self.pending = None          # parity of the step whose gather has been started but not merged yet
+        self.latest = None
         if self.rank == 0:
-            self.gathered = torch.empty((self.world, self.stride), dtype=torch.uint8, device=device)
-            self.slots = list(self.gathered.unbind(0))
-            self.merged = torch.empty(32 + REC_BYTES * self.merged_cap, dtype=torch.uint8, device=device)
+            self.gathered = [torch.empty((self.world, self.stride), dtype=torch.uint8, device=device) for _ in range(2)]
+            self.slots = [list(g.unbind(0)) for g in self.gathered]
+            self.merged = [torch.empty(32 + REC_BYTES * self.merged_cap, dtype=torch.uint8, device=device) for _ in range(2)]
+
+    def _complete(self, k):
+        self.work[k].wait()                                   # current stream waits for the NCCL stream
+        self.work[k] = None
+        if self.rank == 0:
+            self.ctx.merge_gathered(self.gathered[k], self.world, self.stride, self.merged[k], self.merged_cap)
+            self.latest = self.merged[k]
 
     def run(self):
-        """call after ctx.process_device(); returns the merged block (torch.uint8, device) on rank 0, None elsewhere"""
+        """call after ctx.process_device(); returns the merged block of the PREVIOUS step on rank 0 (None on the first
+        call and on other ranks).  The block of this step becomes available after the next run() or flush()."""
         import torch.distributed as dist
 
+        k = self.step & 1
+        self.step += 1
+        self.send[k].copy_(self.local)                        # snapshot: the next batch overwrites the result block
         dst = dist.get_global_rank(self.group, 0) if self.group is not None else 0
-        dist.gather(self.local, gather_list=self.slots if self.rank == 0 else None, dst=dst, group=self.group)
-        if self.rank != 0:
-            return None
-        self.ctx.merge_gathered(self.gathered, self.world, self.stride, self.merged, self.merged_cap)
-        return self.merged
+        self.work[k] = dist.gather(self.send[k], gather_list=self.slots[k] if self.rank == 0 else None, dst=dst,
+                                   group=self.group, async_op=True)
+        prev, self.pending = self.pending, k
+        if prev is not None:
+            self._complete(prev)
+        return self.latest if self.rank == 0 else None
+
+    def flush(self):
+        """completes the outstanding exchange; returns the merged block of the last step on rank 0"""
+        if self.pending is not None:
+            self._complete(self.pending)
+            self.pending = None
+        return self.latest if self.rank == 0 else None
 
     def read(self, det_dtype):
         """rank 0: (records, header) of the last merged block on the host (synchronises)"""
-        m = self.merged.cpu().numpy()
+        self.flush()
+        m = self.latest.cpu().numpy()
         header = m[:32].view(np.uint32).copy()
         n = int(header[0])
         return np.frombuffer(m[32:32 + REC_BYTES * n].tobytes(), dtype=det_dtype), header

@@ -54,6 +54,19 @@ double mmw_legacy_process_frame(const short *frame_host, const double *base_fram
 int mmw_legacy_process_frames(const short *frames_host, int n_frames, const double *base_frame_host, int size,
                               double *distances, int *raw_indices);
 
+/* Same chain for frames already resident in HBM (frames_dev: n_frames * 102 400 int16, device pointer); results stay
+ * on the device (raw_dev: n_frames ints) — asynchronous on the legacy stream, for device-timed throughput. */
+int mmw_legacy_process_device(const short *frames_dev, int n_frames, const double *base_frame_host, int *raw_dev);
+/* Blocks until everything queued by mmw_legacy_process_device has finished. */
+int mmw_legacy_sync(void);
+/* metres from a raw arg-max bin, operation for operation the reference's formula (acceleration.cu:521-523) */
+double mmw_legacy_distance_from_raw(int raw_index);
+
+/* The reference's cudaTiming() loop (cudaBenchMarking.cpp:334-395) in one call: opens the capture at `path`, takes
+ * rx0 of frame 0 as the base frame (:357-365), runs every later frame and stores its distance.  distances[] /
+ * raw_indices[] (optional) hold up to `capacity` results; *n_frames receives the number of frames processed. */
+int mmw_legacy_process_file(const char *path, double *distances, int *raw_indices, int capacity, int *n_frames);
+
 /* Copies the 16 384-point spectrum (complex64, natural order) of the last frame processed through
  * either entry point to `out` (16384 * 2 floats). For parity tests. */
 int mmw_legacy_copy_spectrum(float *out);

@@ -95,8 +95,17 @@ int mmw_get_info(const mmw_ctx *ctx, mmw_info *info);
 int mmw_set_windows(mmw_ctx *ctx, const float *win_range, const float *win_doppler);
 /* copies the tables currently in use back to the host (either pointer may be NULL) */
 int mmw_get_windows(const mmw_ctx *ctx, float *win_range, float *win_doppler);
+/* Static-clutter removal: `base_host` is one frame in capture format (2*S*C*A int16); it is subtracted sample by
+ * sample, in integers, from every frame before the range window — the reference's base-frame subtraction
+ * (acceleration.cu:152-166, cudaBenchMarking.cpp:277-280: rx0 of frame 0) applied to every antenna.  NULL turns it off. */
+int mmw_set_base_frame(mmw_ctx *ctx, const int16_t *base_host);
 /* value added to mmw_detection.frame (the global index of the batch's first frame on this GPU) */
 int mmw_set_frame_offset(mmw_ctx *ctx, uint32_t first_frame);
+
+/* CUDA-graph mode for launch-bound use (one or a few frames per call, e.g. per-sensor streaming): the launch sequence
+ * of a batch is captured once per distinct (capture address, n_frames, frame offset, base frame, stream) and replayed
+ * with a single cudaGraphLaunch.  Off by default; results are identical either way. */
+int mmw_set_graph_mode(mmw_ctx *ctx, int enable);
 
 /* The CUDA stream every call of this context runs on (a cudaStream_t). */
 void *mmw_stream(mmw_ctx *ctx);
@@ -134,6 +143,41 @@ int mmw_device_result_block(mmw_ctx *ctx, const void **block, long long *capacit
  * stream; one kernel. */
 int mmw_merge_gathered(mmw_ctx *ctx, const void *gathered_dev, int n_ranks, long long stride_bytes,
                        void *merged_dev, int merged_capacity);
+
+/* ---- capture-file ingest (the caller side of the boundary: the fopen/fread loop of cudaBenchMarking.cpp:339-378) ----
+ * Reads a raw capture (frames of 2*S*C*A little-endian int16, no header — the fhy_direct.bin format) from `path`,
+ * starting at frame `first_frame`, at most `max_frames` frames (<= 0: to the end of the file), and runs the chain over
+ * it in batches of the context's max_frames.  The file is read into pinned double buffers so that the fread of batch
+ * k+1 overlaps the H2D copy and kernels of batch k.  mmw_detection.frame counts from the start of the FILE.
+ * A trailing partial frame is zero-filled and processed (the reference passes the short count on and processes the
+ * frame anyway, cudaBenchMarking.cpp:374-377).  use_first_as_base != 0: the first frame read becomes the base frame
+ * (mmw_set_base_frame) and is not itself processed — the reference's cudaTiming() convention (:357-365).
+ * *n_frames_done receives the number of frames processed.  Returns MMW_OK, MMW_ERR_OVERFLOW (list truncated) or an
+ * error (MMW_ERR_ARG if the file cannot be opened). */
+int mmw_process_capture_file(mmw_ctx *ctx, const char *path, long long first_frame, int max_frames, int use_first_as_base,
+                             mmw_detection *dets, int det_capacity, int *n_det, int *n_frames_done);
+
+/* ---- detections in physical units ----
+ * The reference declares the radar constants for exactly this but only ever computes a range (cudaBenchMarking.cpp:
+ * 10-19, 301-303).  Host arithmetic on the (small) detection list; no device work. */
+typedef struct mmw_radar_params {
+    double f0_hz;            /* carrier, 77e9           (cudaBenchMarking.cpp:10  F0) */
+    double slope_hz_per_s;   /* chirp slope, 5.987e12   (:11 mu)                      */
+    double fs_hz;            /* ADC sample rate, 2e6    (:13 Fs)                      */
+    double chirp_period_s;   /* chirp repetition, 64e-6 (:15 Tr)                      */
+    double light_speed;      /* 3.0e8 as the reference writes it (:12 c)              */
+} mmw_radar_params;
+typedef struct mmw_target {
+    uint32_t frame;
+    float range_m;           /* c * (range_bin * Fs / Sp) / (2 mu) — the reference's distance formula per chirp */
+    float velocity_mps;      /* (lambda / 2) * d' / (Cp * Tr), d' = doppler_bin wrapped to [-Cp/2, Cp/2) */
+    float angle_deg;         /* angle_rad in degrees */
+    float snr_db;            /* 10 log10(power / noise) */
+    uint32_t flags;          /* MMW_FLAG_* of the detection */
+} mmw_target;
+void mmw_default_radar_params(mmw_radar_params *rp);
+/* Sp, Cp: the FFT lengths the detections were made with (mmw_info.Sp / .Cp) */
+int mmw_to_physical(const mmw_radar_params *rp, int Sp, int Cp, const mmw_detection *dets, int n, mmw_target *out);
 
 /* Intermediates of one frame of the last batch, copied to the host in canonical layouts
  * (synchronous, not on the hot path):

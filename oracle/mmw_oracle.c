@@ -151,16 +151,24 @@ void orc_hann_periodic(int L, float *w)
  * Packing and frame order follow the reference (cudaBenchMarking.cpp:156-165, :168-180). */
 void orc_range_fft(const int16_t *adc, int S, int C, int A, const float *win_r, orc_cx *rs)
 {
+    orc_range_fft_base(adc, NULL, S, C, A, win_r, rs);
+}
+
+/* same with static-clutter removal: `base` (one frame, same packing) is subtracted sample by sample before the
+ * window — the reference's base-frame subtraction (cudaBenchMarking.cpp:277-280) for every antenna */
+void orc_range_fft_base(const int16_t *adc, const int16_t *base, int S, int C, int A, const float *win_r, orc_cx *rs)
+{
     const int Sp = orc_next_pow2(S);
     orc_cx *row = (orc_cx *)malloc((size_t)Sp * sizeof(orc_cx));
     for (int c = 0; c < C; ++c)
         for (int a = 0; a < A; ++a) {
             const int16_t *src = adc + ((long)c * A + a) * S * 2;
+            const int16_t *bsrc = base ? base + ((long)c * A + a) * S * 2 : NULL;
             for (int s = 0; s < S; ++s) {
-                const int16_t *q = src + 4 * (s >> 1) + (s & 1);
+                const long o = 4 * (s >> 1) + (s & 1);
                 double w = (double)win_r[s];
-                row[s].re = (double)q[0] * w;
-                row[s].im = (double)q[2] * w;
+                row[s].re = ((double)src[o] - (bsrc ? (double)bsrc[o] : 0.0)) * w;
+                row[s].im = ((double)src[o + 2] - (bsrc ? (double)bsrc[o + 2] : 0.0)) * w;
             }
             for (int s = S; s < Sp; ++s) row[s].re = row[s].im = 0;
             orc_fft(Sp, row);
@@ -301,6 +309,8 @@ static void scratch_free(orc_scratch *w)
 }
 
 /* one frame; per-thread scratch is reused across frames (the caller's optional output buffers win) */
+static const int16_t *g_base_frame = NULL;   /* set by orc_process_frames_base for the duration of the call */
+
 static long process_one(const int16_t *adc, int f, int S, int C, int A,
                         const float *win_r, const float *win_d,
                         const orc_cfar_params *p, double lambda_over_d,
@@ -318,7 +328,7 @@ static long process_one(const int16_t *adc, int f, int S, int C, int A,
     double *nz = noise_out ? noise_out : w->nz;
     orc_cx *x = w->x;
 
-    orc_range_fft(adc, S, C, A, win_r, rs);
+    orc_range_fft_base(adc, g_base_frame, S, C, A, win_r, rs);
     orc_doppler_fft(rs, Sp, C, A, win_d, dc);
     orc_power(dc, Sp, Cp, A, P);
     orc_cfar(P, Sp, Cp, p, mask, nz);
@@ -393,5 +403,20 @@ long orc_process_frames(const int16_t *adc, int n_frames, int S, int C, int A,
     free(cnt);
     free(tot);
     (void)n_threads;
+    return n;
+}
+
+/* orc_process_frames with static-clutter removal (base = one frame or NULL); not re-entrant */
+long orc_process_frames_base(const int16_t *adc, const int16_t *base, int n_frames, int S, int C, int A,
+                             const float *win_r, const float *win_d,
+                             const orc_cfar_params *p, double lambda_over_d,
+                             orc_detection *dets, long det_cap, long *n_total,
+                             orc_cx *rs_out, orc_cx *dc_out, double *P_out,
+                             uint8_t *mask_out, double *noise_out, int n_threads)
+{
+    g_base_frame = base;
+    long n = orc_process_frames(adc, n_frames, S, C, A, win_r, win_d, p, lambda_over_d, dets, det_cap, n_total,
+                                rs_out, dc_out, P_out, mask_out, noise_out, n_threads);
+    g_base_frame = NULL;
     return n;
 }

@@ -75,6 +75,8 @@ void orc_hann_periodic(int L, float *w);
  * The Doppler window is NOT applied here. */
 void orc_range_fft(const int16_t *adc, int S, int C, int A,
                    const float *win_r, orc_cx *rs);
+void orc_range_fft_base(const int16_t *adc, const int16_t *base, int S, int C, int A,
+                        const float *win_r, orc_cx *rs);
 /* dc: [A][Sp][Cp] complex (Cp = nextPow2(C)); Doppler window applied over c<C, zero pad to Cp */
 void orc_doppler_fft(const orc_cx *rs, int Sp, int C, int A,
                      const float *win_d, orc_cx *dc);
@@ -102,6 +104,15 @@ long orc_process_frames(const int16_t *adc, int n_frames, int S, int C, int A,
                         orc_cx *rs_out, orc_cx *dc_out, double *P_out,
                         uint8_t *mask_out, double *noise_out,
                         int n_threads);
+
+/* same with static-clutter removal: base = one frame in capture format subtracted before the window, or NULL */
+long orc_process_frames_base(const int16_t *adc, const int16_t *base, int n_frames, int S, int C, int A,
+                             const float *win_r, const float *win_d,
+                             const orc_cfar_params *p, double lambda_over_d,
+                             orc_detection *dets, long det_cap, long *n_total,
+                             orc_cx *rs_out, orc_cx *dc_out, double *P_out,
+                             uint8_t *mask_out, double *noise_out,
+                             int n_threads);
 
 #ifdef __cplusplus
 }

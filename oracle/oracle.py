@@ -97,6 +97,8 @@ def lib():
             _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.POINTER(CfarParams), C.c_double,
             _vp, C.c_long, C.POINTER(C.c_long), _vp, _vp, _vp, _vp, _vp, C.c_int,
         ]
+        L.orc_process_frames_base.restype = C.c_long
+        L.orc_process_frames_base.argtypes = [_vp] + L.orc_process_frames.argtypes
         _lib = L
     return _lib
 
@@ -180,9 +182,11 @@ def angle_fft_size(A: int) -> int:
 
 
 def process_frames(adc, n_frames, S, C_, A, win_r, win_d, guard=(2, 2), train=(8, 4), alpha=15.0,
-                   lambda_over_d=2.0, det_cap_per_frame=4096, want=(), n_threads=1):
-    """Whole chain.  `want` may name 'rs', 'dc', 'P', 'mask', 'noise' to get the intermediates."""
+                   lambda_over_d=2.0, det_cap_per_frame=4096, want=(), n_threads=1, base=None):
+    """Whole chain.  `want` may name 'rs', 'dc', 'P', 'mask', 'noise' to get the intermediates.
+    base: one frame (int16, capture format) subtracted from every frame before the range window, or None."""
     adc = np.ascontiguousarray(adc, np.int16)
+    base = None if base is None else np.ascontiguousarray(base, np.int16).reshape(-1)
     Sp, Cp = next_pow2(S), next_pow2(C_)
     prm = CfarParams(guard[0], guard[1], train[0], train[1], float(alpha))
     dets = np.zeros(det_cap_per_frame * max(n_frames, 1), DET_DTYPE)
@@ -198,8 +202,8 @@ def process_frames(adc, n_frames, S, C_, A, win_r, win_d, guard=(2, 2), train=(8
     if "noise" in want:
         out["noise"] = np.empty((n_frames, Sp, Cp), np.float64)
     total = C.c_long(0)
-    n = lib().orc_process_frames(
-        _ptr(adc), n_frames, S, C_, A,
+    n = lib().orc_process_frames_base(
+        _ptr(adc), _ptr(base), n_frames, S, C_, A,
         _ptr(np.ascontiguousarray(win_r, np.float32)), _ptr(np.ascontiguousarray(win_d, np.float32)),
         C.byref(prm), float(lambda_over_d), _ptr(dets), dets.size, C.byref(total),
         _ptr(out.get("rs")), _ptr(out.get("dc")), _ptr(out.get("P")), _ptr(out.get("mask")), _ptr(out.get("noise")),

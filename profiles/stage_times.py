@@ -10,7 +10,7 @@ import torch  # noqa: E402
 import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
-SHAPES = {"cfg3": (512, 256, 12, 64), "cfg2": (256, 128, 4, 1024), "cfg4": (1024, 512, 192, 2), "cfg5": (256, 128, 12, 64),
+SHAPES = {"cfg3": (512, 256, 12, 64), "cfg2": (256, 128, 4, 1024), "cfg4": (1024, 512, 192, 4), "cfg5": (256, 128, 12, 64),
           "legacy": (100, 128, 4, 256)}
 dev = torch.device("cuda", 0)
 for wl in (sys.argv[1:] or ["cfg3", "cfg2"]):
