@@ -241,8 +241,8 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     if ((rc = dev_alloc(c, &c->d_keys, (size_t)F * cfg->max_det_per_frame))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_counts, (size_t)F))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_offsets, (size_t)F + 1))) return fail(rc);
-    if ((rc = dev_alloc(c, &c->d_ticket, (size_t)1))) return fail(rc);
-    if (cudaMemset(c->d_ticket, 0, sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
+    if ((rc = dev_alloc(c, &c->d_ticket, (size_t)2))) return fail(rc);
+    if (cudaMemset(c->d_ticket, 0, 2 * sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     c->dense_cap = F * cfg->max_det_per_frame;
     const size_t result_bytes = kResultHeaderBytes + (size_t)c->dense_cap * sizeof(mmw_detection);
     if ((rc = dev_alloc(c, &c->d_result, result_bytes))) return fail(rc);

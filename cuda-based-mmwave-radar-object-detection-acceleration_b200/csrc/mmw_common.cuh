@@ -104,7 +104,7 @@ struct DetectBuffers {
     uint32_t *counts;       // [F]    true hit count per frame
     uint32_t *offsets;      // [F+1]  exclusive scan of min(count, max_det)
     uint32_t *header;       // {n_written, n_total, n_frames, overflow}
-    unsigned int *ticket;   // last-CTA-done counter (self-resetting)
+    unsigned int *ticket;   // [0] last-CTA-done counter of list_kernel, [1] work cursor of measure_kernel (both self-resetting)
     mmw_detection *dense;   // ordered detection list of the batch
 };
 cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, cudaStream_t st);

@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
     constexpr int SUBS = 32 / BT;
     constexpr int NSLOT = NW * SUBS;
     constexpr int LR1 = ilog2(R1), LR2 = ilog2(R2);
-
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     float2 *tw = reinterpret_cast<float2 *>(smem + L::kOffTw);
@@ -85,7 +84,7 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
     const int C = CT ? CT : p.C;
     const int nct = (C + BT - 1) / BT;
 
-    auto issue = [&](int tile, int it) {    // warp 0: stage the BT int16 rows of `tile` (the it-th tile of this CTA)
+    auto issue = [&](int tile, int it) {    // one warp: stage the BT int16 rows of `tile` (the it-th tile of this CTA)
         const int ct = tile % nct, fa = tile / nct;
         const int a = fa % A, f = fa / A;
         const int c0 = ct * BT;
@@ -206,7 +205,9 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
             }
         }
         __syncthreads();
-        // single staging buffer: it is consumed now, prefetch the next tile behind pass 2
+        // single staging buffer: it is consumed now, prefetch the next tile behind pass 2.  (Refilling it earlier — as
+        // soon as the last warp has pulled its pass-1 inputs into registers — removes the wait on the copy but not a
+        // microsecond of run time: the stall moves to the barrier, profiles/experiments/r1_k1_early_release.md.)
         if (NSTAGE == 1 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
 
         // ---- pass 2: R1 butterflies of radix R2 on contiguous runs; outputs go straight to HBM ----

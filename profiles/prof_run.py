@@ -10,7 +10,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
-S, C, A, F = {"cfg3": (512, 256, 12, 32), "cfg2": (256, 128, 4, 512)}[wl]
+S, C, A, F = {"cfg3": (512, 256, 12, 64), "cfg2": (256, 128, 4, 1024)}[wl]
 dev = torch.device("cuda", 0)
 adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=3)
 torch.cuda.synchronize()

@@ -22,3 +22,24 @@ def test_unmodified_reference_caller_runs_against_our_library(pkg, tmp_path):
     assert out.count("Inner CUDA Timing") == 89                     # one line per frame, as acceleration.cu:533
     assert "Total Time for 89 frames" in out and "cuda totalTime" in out and "cuda inner time" in out
     print("\n" + "\n".join(l for l in out.splitlines() if "Inner CUDA" not in l))
+
+
+def test_verification_harness_of_the_reference_main(pkg, orc, tmp_path):
+    """the CPU-vs-GPU check the reference left commented out (cudaBenchMarking.cpp:405-419,
+    tolerance 1e-5), as a C++ program calling cudaProcessing() the way cudaTiming() does."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "verify_legacy"
+    cmd = ["/usr/bin/g++", "-O2", "-o", str(exe), os.path.join(root, "tests", "verify_legacy.cpp"),
+           "-I", os.path.join(root, "include"), "-I", os.path.join(root, "oracle"),
+           pkg.api.library_path(), orc.ORACLE_SO, "-Wl,-rpath," + os.path.dirname(pkg.api.library_path()),
+           "-Wl,-rpath," + os.path.dirname(orc.ORACLE_SO)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for seed, moving in ((0, False), (7, True)):
+        cap = pkg.synth.legacy_capture(40, seed=seed, moving=moving)
+        path = tmp_path / f"cap{seed}.bin"
+        cap.tofile(path)
+        r = subprocess.run([str(exe), str(path)], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, MMW_LEGACY_QUIET="1"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "verified 39 frames, 0 mismatches" in r.stdout

@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4          # relative to the maximum of the array being compared
 NEAR = 1e-5         # |P - thr| <= NEAR * thr  -> cell is "at threshold", excluded from the bit-exact claim
 
-SHAPES = [(64, 64, 2), (100, 128, 4), (128, 64, 12), (256, 128, 4), (512, 256, 12), (1024, 64, 2), (64, 1024, 1), (256, 512, 3)]
+# the last two exercise the 256-point angle FFT (A > 64: the cfg4 imaging array) and an odd antenna count
+SHAPES = [(64, 64, 2), (100, 128, 4), (128, 64, 12), (256, 128, 4), (512, 256, 12), (1024, 64, 2), (64, 1024, 1), (256, 512, 3),
+          (64, 64, 192), (128, 128, 65)]
 
 
 def relmax(a, b):
@@ -109,6 +111,30 @@ def test_cfar_and_detections(pkg, orc, cases, shape, keep):
               if (i or j) and 0 <= k[1] + i < P.shape[0] and ref["mask"][k[0]][k[1] + i, (k[2] + j) % P.shape[1]]]
         if all(abs(v - P[k[1], k[2]]) > 1e-4 * P[k[1], k[2]] for v in nb) and not any(near[k[0]][max(0, k[1] - 1):k[1] + 2].ravel()):
             assert (d["flags"] & 1) == (o["flags"] & 1)
+
+
+@pytest.mark.parametrize("guard,train,alpha", [((0, 0), (1, 1), 6.0), ((1, 3), (5, 2), 10.0), ((4, 1), (12, 7), 12.0), ((2, 2), (8, 4), 4.0)])
+def test_cfar_geometries(pkg, orc, guard, train, alpha):
+    """non-default guard / training windows take the run-time-bound CFAR path; range edges clamp, Doppler wraps"""
+    S, C, A, F = 128, 64, 4, 2
+    adc = pkg.synth.cube_batch(F, S, C, A, cfg=11, n_targets=6)
+    wr, wd = orc.hann_periodic(S), orc.hann_periodic(C)
+    ref = orc.process_frames(adc, F, S, C, A, wr, wd, guard=guard, train=train, alpha=alpha, want=("P", "mask", "noise"))
+    thr = alpha * ref["noise"]
+    near = np.abs(ref["P"] - thr) <= NEAR * thr
+    with pkg.RadarContext(S, C, A, F, cfar_guard=guard, cfar_train=train, cfar_alpha=alpha, max_det_per_frame=8192) as ctx:
+        dets, ov = ctx.process_host(adc, F)
+        for f in range(F):
+            m = ctx.cfar_mask(f)
+            assert not ((m != ref["mask"][f]) & ~near[f]).any()
+            edge = np.r_[0:train[0] + guard[0] + 1, S - train[0] - guard[0] - 1:S]     # the clamped range rows in particular
+            assert not ((m[edge] != ref["mask"][f][edge]) & ~near[f][edge]).any()
+    by = {(int(d["frame"]), int(d["range_bin"]), int(d["doppler_bin"])): d for d in ref["dets"]}
+    assert len(dets) > 0 and not ov
+    for d in dets:
+        k = (int(d["frame"]), int(d["range_bin"]), int(d["doppler_bin"]))
+        if k in by:
+            assert abs(d["noise"] - by[k]["noise"]) <= 1e-3 * by[k]["noise"] + 1e-7 * ref["P"][k[0]].max()
 
 
 def test_detection_list_overflow_is_ordered_and_counted(pkg, orc):
