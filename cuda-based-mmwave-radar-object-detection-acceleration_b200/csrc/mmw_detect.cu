@@ -313,7 +313,7 @@ __device__ __forceinline__ float warp_sum(float v)
 // range bin are consecutive.  In fused mode each of them needs one Doppler bin of the SAME A x C block of the range
 // spectrum; a run of equal range bin is cut into chunks of kMeasG detections, one warp per chunk, and the warp reads
 // every row once for all the detections of its chunk.
-__global__ void __launch_bounds__(kMeasNT, 3) measure_kernel(PlanDev p, const float2 *__restrict__ rs, const float2 *__restrict__ cube,
+__global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float2 *__restrict__ rs, const float2 *__restrict__ cube,
                                                           const float *__restrict__ pmap, const float *__restrict__ noise_map,
                                                           const uint32_t *__restrict__ mask, const uint32_t *__restrict__ keys,
                                                           const uint32_t *__restrict__ offsets, mmw_detection *__restrict__ dense,
@@ -341,172 +341,172 @@ __global__ void __launch_bounds__(kMeasNT, 3) measure_kernel(PlanDev p, const fl
         if (lane == 0) gblk = atomicAdd(cursor, blk);
         gblk = __shfl_sync(0xffffffffu, gblk, 0);
         if (gblk >= total) break;
-      for (uint32_t g0 = gblk; g0 < min(gblk + blk, total); ++g0) {
-        if (g0 < fbeg || g0 >= fend_raw) {
-            // frame of detection g0: largest f with offsets[f] <= g0
-            int lo = 0, hi = n_frames - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (offsets[mid] <= g0) lo = mid; else hi = mid - 1;
+        for (uint32_t g0 = gblk; g0 < min(gblk + blk, total); ++g0) {
+            if (g0 < fbeg || g0 >= fend_raw) {
+                // frame of detection g0: largest f with offsets[f] <= g0
+                int lo = 0, hi = n_frames - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (offsets[mid] <= g0) lo = mid; else hi = mid - 1;
+                }
+                f = lo;
+                fbeg = offsets[f];
+                fend_raw = offsets[f + 1];
             }
-            f = lo;
-            fbeg = offsets[f];
-            fend_raw = offsets[f + 1];
-        }
-        const uint32_t fend = min(fend_raw, total);
-        const uint32_t *kf = keys + (size_t)f * p.max_det - fbeg;  // kf[g] = key of list position g
-        const uint32_t key0 = kf[g0];
-        const int r = key0 >> 16;
-        // position of g0 inside its run of equal range bin; every kMeasG-th detection of a run heads a chunk and its
-        // warp measures the chunk (the others return: their chunk head does them).  The neighbouring keys are read 32
-        // at a time, one per lane, so that finding the run costs one memory round trip instead of one per element.
-        uint32_t back = 0;
-        for (uint32_t base = g0;;) {                              // 32 predecessors per round
-            const bool same = base >= fbeg + 1 + lane && (int)(kf[base - 1 - lane] >> 16) == r;
-            const uint32_t m = __ballot_sync(0xffffffffu, same);
-            const uint32_t n = m == 0xffffffffu ? 32u : (uint32_t)(__ffs(~m) - 1);
-            back += n;
-            if (n < 32u) break;
-            base -= 32u;
-        }
-        if (back % kMeasG != 0) continue;
-        const uint32_t mykey = g0 + lane < fend ? kf[g0 + lane] : 0xffffffffu;      // lane j: key of list position g0 + j
-        const uint32_t fm = __ballot_sync(0xffffffffu, g0 + lane < fend && (int)(mykey >> 16) == r);
-        const int ng = min(kMeasG, fm == 0xffffffffu ? 32 : __ffs(~fm) - 1);
+            const uint32_t fend = min(fend_raw, total);
+            const uint32_t *kf = keys + (size_t)f * p.max_det - fbeg;  // kf[g] = key of list position g
+            const uint32_t key0 = kf[g0];
+            const int r = key0 >> 16;
+            // position of g0 inside its run of equal range bin; every kMeasG-th detection of a run heads a chunk and its
+            // warp measures the chunk (the others return: their chunk head does them).  The neighbouring keys are read 32
+            // at a time, one per lane, so that finding the run costs one memory round trip instead of one per element.
+            uint32_t back = 0;
+            for (uint32_t base = g0;;) {                              // 32 predecessors per round
+                const bool same = base >= fbeg + 1 + lane && (int)(kf[base - 1 - lane] >> 16) == r;
+                const uint32_t m = __ballot_sync(0xffffffffu, same);
+                const uint32_t n = m == 0xffffffffu ? 32u : (uint32_t)(__ffs(~m) - 1);
+                back += n;
+                if (n < 32u) break;
+                base -= 32u;
+            }
+            if (back % kMeasG != 0) continue;
+            const uint32_t mykey = g0 + lane < fend ? kf[g0 + lane] : 0xffffffffu;      // lane j: key of list position g0 + j
+            const uint32_t fm = __ballot_sync(0xffffffffu, g0 + lane < fend && (int)(mykey >> 16) == r);
+            const int ng = min(kMeasG, fm == 0xffffffffu ? 32 : __ffs(~fm) - 1);
 
-        const float *pf = pmap + (size_t)f * Cp * Sp;
-        const uint32_t *mf = mask + (size_t)f * (Cp / 32) * Sp;
+            const float *pf = pmap + (size_t)f * Cp * Sp;
+            const uint32_t *mf = mask + (size_t)f * (Cp / 32) * Sp;
 
-        {
-            const uint32_t gb = g0;
-            int dj[kMeasG];
+            {
+                const uint32_t gb = g0;
+                int dj[kMeasG];
 #pragma unroll
-            for (int j = 0; j < kMeasG; ++j) dj[j] = (int)(__shfl_sync(0xffffffffu, mykey, min(j, ng - 1)) & 0xffffu);
+                for (int j = 0; j < kMeasG; ++j) dj[j] = (int)(__shfl_sync(0xffffffffu, mykey, min(j, ng - 1)) & 0xffffu);
 
-            // antenna snapshots at (r, d_j)
-            if (cube != nullptr) {
-#pragma unroll
-                for (int j = 0; j < kMeasG; ++j)
-                    if (j < ng)
-                        for (int a = lane; a < A; a += 32) xw[j * A + a] = cube[(((size_t)f * A + a) * Cp + dj[j]) * Sp + r];
-            } else {
-                // fused mode: Doppler bins d_j of every antenna straight from the (already windowed) range spectrum.
-                // kMeasQ antennas x 256 chirps (kMeasQ * 8 independent 8-byte loads per lane) are pulled into registers
-                // before anything is consumed — the kernel is bound by memory latency, not by arithmetic — and every
-                // value then feeds all the chunk's detections.  The summation order per (antenna, detection) is fixed:
-                // lane-strided partial sums in ascending chirp order, then the xor-butterfly over lanes.
-                const float2 *src0 = rs + (((size_t)f * A) * Sp + r) * (size_t)C;
-                const size_t astride = (size_t)Sp * C;
-                for (int a0 = 0; a0 < A; a0 += kMeasQ) {
-                    float sx[kMeasG][kMeasQ], sy[kMeasG][kMeasQ];
+                // antenna snapshots at (r, d_j)
+                if (cube != nullptr) {
 #pragma unroll
                     for (int j = 0; j < kMeasG; ++j)
+                        if (j < ng)
+                            for (int a = lane; a < A; a += 32) xw[j * A + a] = cube[(((size_t)f * A + a) * Cp + dj[j]) * Sp + r];
+                } else {
+                    // fused mode: Doppler bins d_j of every antenna straight from the (already windowed) range spectrum.
+                    // kMeasQ antennas x 256 chirps (kMeasQ * 8 independent 8-byte loads per lane) are pulled into registers
+                    // before anything is consumed — the kernel is bound by memory latency, not by arithmetic — and every
+                    // value then feeds all the chunk's detections.  The summation order per (antenna, detection) is fixed:
+                    // lane-strided partial sums in ascending chirp order, then the xor-butterfly over lanes.
+                    const float2 *src0 = rs + (((size_t)f * A) * Sp + r) * (size_t)C;
+                    const size_t astride = (size_t)Sp * C;
+                    for (int a0 = 0; a0 < A; a0 += kMeasQ) {
+                        float sx[kMeasG][kMeasQ], sy[kMeasG][kMeasQ];
 #pragma unroll
-                        for (int q = 0; q < kMeasQ; ++q) sx[j][q] = sy[j][q] = 0.f;
-                    for (int cc0 = 0; cc0 < C; cc0 += 256) {
-                        float2 v[kMeasQ][8];
+                        for (int j = 0; j < kMeasG; ++j)
 #pragma unroll
-                        for (int q = 0; q < kMeasQ; ++q) {
-                            const float2 *sa = src0 + (size_t)min(a0 + q, A - 1) * astride;
+                            for (int q = 0; q < kMeasQ; ++q) sx[j][q] = sy[j][q] = 0.f;
+                        for (int cc0 = 0; cc0 < C; cc0 += 256) {
+                            float2 v[kMeasQ][8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int c = cc0 + lane + 32 * i;
-                                v[q][i] = c < C ? sa[c] : make_float2(0.f, 0.f);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < kMeasG; ++j) {
-                            if (j < ng) {
-                                const int d = dj[j];
+                            for (int q = 0; q < kMeasQ; ++q) {
+                                const float2 *sa = src0 + (size_t)min(a0 + q, A - 1) * astride;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const int c = cc0 + lane + 32 * i;
-                                    const float2 w = p.tw_d[(c * d) & (Cp - 1)];
+                                    v[q][i] = c < C ? sa[c] : make_float2(0.f, 0.f);
+                                }
+                            }
 #pragma unroll
-                                    for (int q = 0; q < kMeasQ; ++q) {
-                                        sx[j][q] += v[q][i].x * w.x - v[q][i].y * w.y;
-                                        sy[j][q] += v[q][i].x * w.y + v[q][i].y * w.x;
+                            for (int j = 0; j < kMeasG; ++j) {
+                                if (j < ng) {
+                                    const int d = dj[j];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const int c = cc0 + lane + 32 * i;
+                                        const float2 w = p.tw_d[(c * d) & (Cp - 1)];
+#pragma unroll
+                                        for (int q = 0; q < kMeasQ; ++q) {
+                                            sx[j][q] += v[q][i].x * w.x - v[q][i].y * w.y;
+                                            sy[j][q] += v[q][i].x * w.y + v[q][i].y * w.x;
+                                        }
                                     }
                                 }
                             }
                         }
+#pragma unroll
+                        for (int j = 0; j < kMeasG; ++j)
+#pragma unroll
+                            for (int q = 0; q < kMeasQ; ++q) {
+                                const float tx = warp_sum(sx[j][q]), ty = warp_sum(sy[j][q]);
+                                if (lane == 0 && j < ng && a0 + q < A) xw[j * A + a0 + q] = make_float2(tx, ty);
+                            }
                     }
+                }
+                __syncwarp();
+
 #pragma unroll
-                    for (int j = 0; j < kMeasG; ++j)
-#pragma unroll
-                        for (int q = 0; q < kMeasQ; ++q) {
-                            const float tx = warp_sum(sx[j][q]), ty = warp_sum(sy[j][q]);
-                            if (lane == 0 && j < ng && a0 + q < A) xw[j * A + a0 + q] = make_float2(tx, ty);
+                for (int j = 0; j < kMeasG; ++j) {
+                    if (j >= ng) break;
+                    const uint32_t g = gb + j;
+                    const int d = dj[j];
+                    const uint32_t key = ((uint32_t)r << 16) | (uint32_t)d;
+                    const float pw = pf[(size_t)d * Sp + r];
+                    const float noise = noise_map[((size_t)f * Cp + d) * Sp + r];
+
+                    // 3x3 grouping among detected cells (Doppler wraps, range clamps; ties -> lowest (r,d))
+                    bool worse = false;
+                    if (lane < 9 && lane != 4) {
+                        const int rr = r + lane / 3 - 1;
+                        const int dd = (d + lane % 3 - 1 + Cp) & (Cp - 1);
+                        if (rr >= 0 && rr < Sp) {
+                            const uint32_t w = mf[(size_t)(dd >> 5) * Sp + rr];
+                            if ((w >> (dd & 31)) & 1u) {
+                                const float pn = pf[(size_t)dd * Sp + rr];
+                                const uint32_t kn = ((uint32_t)rr << 16) | (uint32_t)dd;
+                                worse = (pn > pw) || (pn == pw && kn < key);
+                            }
                         }
-                }
-            }
-            __syncwarp();
+                    }
+                    const bool is_peak = __ballot_sync(0xffffffffu, worse) == 0u;
 
-#pragma unroll
-            for (int j = 0; j < kMeasG; ++j) {
-                if (j >= ng) break;
-                const uint32_t g = gb + j;
-                const int d = dj[j];
-                const uint32_t key = ((uint32_t)r << 16) | (uint32_t)d;
-                const float pw = pf[(size_t)d * Sp + r];
-                const float noise = noise_map[((size_t)f * Cp + d) * Sp + r];
-
-                // 3x3 grouping among detected cells (Doppler wraps, range clamps; ties -> lowest (r,d))
-                bool worse = false;
-                if (lane < 9 && lane != 4) {
-                    const int rr = r + lane / 3 - 1;
-                    const int dd = (d + lane % 3 - 1 + Cp) & (Cp - 1);
-                    if (rr >= 0 && rr < Sp) {
-                        const uint32_t w = mf[(size_t)(dd >> 5) * Sp + rr];
-                        if ((w >> (dd & 31)) & 1u) {
-                            const float pn = pf[(size_t)dd * Sp + rr];
-                            const uint32_t kn = ((uint32_t)rr << 16) | (uint32_t)dd;
-                            worse = (pn > pw) || (pn == pw && kn < key);
+                    // angle spectrum arg-max (strict >, first wins)
+                    const float2 *xj = xw + j * A;
+                    float best = -1.f;
+                    int bestk = 0;
+                    for (int k = lane; k < p.n_theta; k += 32) {
+                        float yx = 0.f, yy = 0.f;
+                        for (int a = 0; a < A; ++a) {
+                            const float2 v = xj[a];
+                            const float2 w = twa[(k * a) & (p.n_theta - 1)];
+                            yx += v.x * w.x - v.y * w.y;
+                            yy += v.x * w.y + v.y * w.x;
                         }
+                        const float m = yx * yx + yy * yy;
+                        if (m > best) { best = m; bestk = k; }
                     }
-                }
-                const bool is_peak = __ballot_sync(0xffffffffu, worse) == 0u;
-
-                // angle spectrum arg-max (strict >, first wins)
-                const float2 *xj = xw + j * A;
-                float best = -1.f;
-                int bestk = 0;
-                for (int k = lane; k < p.n_theta; k += 32) {
-                    float yx = 0.f, yy = 0.f;
-                    for (int a = 0; a < A; ++a) {
-                        const float2 v = xj[a];
-                        const float2 w = twa[(k * a) & (p.n_theta - 1)];
-                        yx += v.x * w.x - v.y * w.y;
-                        yy += v.x * w.y + v.y * w.x;
-                    }
-                    const float m = yx * yx + yy * yy;
-                    if (m > best) { best = m; bestk = k; }
-                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
-                    if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+                        if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+                    }
+                    if (lane == 0) {
+                        const int kw = bestk < p.n_theta / 2 ? bestk : bestk - p.n_theta;
+                        float sn = (float)kw * p.lambda_over_d / (float)p.n_theta;
+                        sn = fminf(1.f, fmaxf(-1.f, sn));
+                        mmw_detection o;
+                        o.frame = (uint32_t)f + p.frame_offset;
+                        o.range_bin = (uint16_t)r;
+                        o.doppler_bin = (uint16_t)d;
+                        o.power = pw;
+                        o.noise = noise;
+                        o.angle_bin = (int16_t)kw;
+                        o.flags = is_peak ? MMW_FLAG_PEAK : 0;
+                        o.angle_rad = asinf(sn);
+                        dense[g] = o;
+                    }
                 }
-                if (lane == 0) {
-                    const int kw = bestk < p.n_theta / 2 ? bestk : bestk - p.n_theta;
-                    float sn = (float)kw * p.lambda_over_d / (float)p.n_theta;
-                    sn = fminf(1.f, fmaxf(-1.f, sn));
-                    mmw_detection o;
-                    o.frame = (uint32_t)f + p.frame_offset;
-                    o.range_bin = (uint16_t)r;
-                    o.doppler_bin = (uint16_t)d;
-                    o.power = pw;
-                    o.noise = noise;
-                    o.angle_bin = (int16_t)kw;
-                    o.flags = is_peak ? MMW_FLAG_PEAK : 0;
-                    o.angle_rad = asinf(sn);
-                    dense[g] = o;
-                }
+                __syncwarp();
             }
-            __syncwarp();
         }
-      }
     }
 }
 

@@ -420,6 +420,156 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
 }
 
 // ---------------------------------------------------------------------------
+// K2w: Doppler FFT with warp-private tiles (fused mode: power map only)
+// ---------------------------------------------------------------------------
+// doppler_fft_kernel above shares a 16-row tile between the warps of a CTA, so the two passes are separated by CTA-wide
+// barriers and all warps of the CTA sit in the same phase (ncu: barrier is the top stall, issue slots < 50 % busy).
+// Here a warp owns its rows outright: lanes = ROWS rows x SUBS butterflies of one row, the hand-over between the passes
+// is a __syncwarp, every warp has its own mbarrier-tracked staging ring, and the 16 warps of an SM drift apart so that one
+// warp's shared-memory latency hides behind another's arithmetic.  Pass 1 runs in place: a thread first pulls all its
+// inputs into registers, and the outputs go back into the same row in a layout padded by one element per R2 so that
+// pass 2 (lanes = different k1 of one row, stride R2) is bank-conflict free.
+template <int N, int R1, int R2>
+struct DopplerWarp {
+    static constexpr int kSubs = (R1 < R2 ? R1 : R2) > 16 ? 16 : (R1 < R2 ? R1 : R2);
+    static constexpr int kRows = 32 / kSubs;
+    static constexpr int kU1 = R2 / kSubs;                           // pass-1 butterflies per thread
+    static constexpr int kU2 = R1 / kSubs;                           // pass-2 butterflies per thread
+    static constexpr int kRowStride = N + R1;                        // float2: N points + one pad per R2
+    static constexpr int kStage = kRows * kRowStride;                // float2 per staging buffer of one warp
+    static constexpr int kOffTw = 512;                               // room for NW * NSTAGE mbarriers
+    static constexpr int bytes(int nw, int nstage) { return kOffTw + 8 * N + nw * nstage * kStage * 8; }
+};
+
+template <int N, int R1, int R2, int NW, bool PAD, int SPT, int NSTAGE>
+__global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p, const float2 *__restrict__ rs, float *__restrict__ pmap,
+                                                                      int n_tiles)
+{
+    static_assert(R1 * R2 == N, "plan");
+    using L = DopplerWarp<N, R1, R2>;
+    constexpr int SUBS = L::kSubs, ROWS = L::kRows, U1 = L::kU1, U2 = L::kU2;
+    constexpr int LR1 = ilog2(R1), LR2 = ilog2(R2);
+    constexpr bool TWREG = U1 * (R1 - 1) <= 16;
+    static_assert(NW * NSTAGE * 8 <= L::kOffTw, "barriers");
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem) + warp * NSTAGE;
+    float2 *tw = reinterpret_cast<float2 *>(smem + L::kOffTw);
+    float2 *ring = reinterpret_cast<float2 *>(smem + L::kOffTw + 8 * N) + (size_t)warp * NSTAGE * L::kStage;
+
+    const int row = lane / SUBS, sub = lane % SUBS;
+    const int C = PAD ? p.C : N, A = p.A;
+    const int Sp = SPT ? SPT : p.Sp;
+    const int nrt = Sp / ROWS;
+    const long long gw = (long long)blockIdx.x * NW + warp, nwarp = (long long)gridDim.x * NW;
+
+    auto issue_step = [&](int q) {                                  // the q-th step of this warp
+        const int itq = q / A, a = q - itq * A;
+        const long long tl = gw + (long long)itq * nwarp;
+        if (tl >= n_tiles) return;
+        const int tile = (int)tl;
+        const int rt = tile % nrt, f = tile / nrt;
+        uint64_t *b = &bar[q % NSTAGE];
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(b, (uint32_t)(ROWS * C * 8));
+        }
+        __syncwarp();
+        if (lane < ROWS) {
+            const float2 *src = rs + (((size_t)f * A + a) * Sp + rt * ROWS + lane) * (size_t)C;
+            bulk_g2s(ring + (size_t)(q % NSTAGE) * L::kStage + lane * L::kRowStride, src, (uint32_t)(C * 8), b);
+        }
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(&bar[i], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < N; i += NW * 32) tw[i] = p.tw1_d[i];
+    __syncthreads();                                                 // the only CTA-wide barrier
+#pragma unroll
+    for (int i = 0; i < NSTAGE - 1; ++i) issue_step(i);
+
+    float2 twr[TWREG ? U1 : 1][TWREG ? R1 - 1 : 1];
+    if constexpr (TWREG) {
+#pragma unroll
+        for (int u = 0; u < U1; ++u)
+#pragma unroll
+            for (int k1 = 1; k1 < R1; ++k1) twr[u][k1 - 1] = tw[tw1_index(sub + u * SUBS, k1, R1)];
+    }
+
+    int q = 0;
+#pragma unroll 1
+    for (long long tl = gw; tl < n_tiles; tl += nwarp) {
+        const int tile = (int)tl;
+        const int rt = tile % nrt, f = tile / nrt;
+        float acc[U2][R2];
+#pragma unroll
+        for (int u = 0; u < U2; ++u)
+#pragma unroll
+            for (int j = 0; j < R2; ++j) acc[u][j] = 0.f;
+
+#pragma unroll 1
+        for (int a = 0; a < A; ++a, ++q) {
+            issue_step(q + NSTAGE - 1);                              // into the buffer step q - 1 has just left
+            mbar_wait(&bar[q % NSTAGE], (uint32_t)((q / NSTAGE) & 1));
+            float2 *r = ring + (size_t)(q % NSTAGE) * L::kStage + row * L::kRowStride;
+
+            // pass 1: all inputs into registers first (the outputs overwrite other threads' inputs)
+            float2 x[U1][R1];
+#pragma unroll
+            for (int u = 0; u < U1; ++u) {
+                const int n2 = sub + u * SUBS;
+#pragma unroll
+                for (int m = 0; m < R1; ++m) {
+                    const int n = n2 + m * R2;
+                    x[u][m] = (!PAD || n < C) ? r[n] : make_float2(0.f, 0.f);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < U1; ++u) {
+                const int n2 = sub + u * SUBS;
+                dft_regs<R1>(x[u]);
+                r[n2] = x[u][0];
+#pragma unroll
+                for (int k1 = 1; k1 < R1; ++k1) {
+                    const float2 w = TWREG ? twr[u][k1 - 1] : tw[tw1_index(n2, k1, R1)];
+                    r[k1 * (R2 + 1) + n2] = cmul(x[u][bitrev(k1, LR1)], w);
+                }
+            }
+            __syncwarp();
+            // pass 2: radix R2 on (padded) contiguous runs; accumulate |X|^2 (ascending antenna order)
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int k1 = sub + u * SUBS;
+                float2 y[R2];
+                const float2 *wi = r + k1 * (R2 + 1);
+#pragma unroll
+                for (int n2 = 0; n2 < R2; ++n2) y[n2] = wi[n2];
+                dft_regs<R2>(y);
+#pragma unroll
+                for (int k2 = 0; k2 < R2; ++k2) {
+                    const float2 v = y[bitrev(k2, LR2)];
+                    acc[u][k2] += v.x * v.x + v.y * v.y;
+                }
+            }
+            __syncwarp();
+        }
+
+        float *po = pmap + (size_t)f * N * Sp + rt * ROWS + row;
+#pragma unroll
+        for (int u = 0; u < U2; ++u) {
+            const int k1 = sub + u * SUBS;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) po[(size_t)(k1 + R1 * k2) * Sp] = acc[u][k2];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // export kernels (not on the hot path)
 // ---------------------------------------------------------------------------
 __global__ void export_cube_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, int A, int Sp, int Cp)
@@ -525,6 +675,35 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
     return cudaGetLastError();
 }
 
+template <int N, int R1, int R2, int NW, bool PAD, int SPT, int NSTAGE>
+static cudaError_t run_doppler_warp_t(const PlanDev &p, const float2 *rs, float *pmap, int n_frames, cudaStream_t st)
+{
+    auto k = doppler_fft_warp_kernel<N, R1, R2, NW, PAD, SPT, NSTAGE>;
+    using L = DopplerWarp<N, R1, R2>;
+    constexpr int bytes = L::bytes(NW, NSTAGE);
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    }
+    const long long tiles = (long long)n_frames * (p.Sp / L::kRows);
+    const long long want = (tiles + NW - 1) / NW;
+    const int grid = (int)(want < (long long)per_sm * sm_count() ? want : (long long)per_sm * sm_count());
+    k<<<grid, NW * 32, bytes, st>>>(p, rs, pmap, (int)tiles);
+    return cudaGetLastError();
+}
+
+template <int N, int R1, int R2, int NW, int SP0, int NSTAGE>
+static cudaError_t run_doppler_warp(const PlanDev &p, const float2 *rs, float *pmap, int n_frames, cudaStream_t st)
+{
+    if (p.C == N) {
+        if (SP0 && p.Sp == SP0) return run_doppler_warp_t<N, R1, R2, NW, false, SP0, NSTAGE>(p, rs, pmap, n_frames, st);
+        return run_doppler_warp_t<N, R1, R2, NW, false, 0, NSTAGE>(p, rs, pmap, n_frames, st);
+    }
+    return run_doppler_warp_t<N, R1, R2, NW, true, 0, NSTAGE>(p, rs, pmap, n_frames, st);
+}
+
 template <int N, int R1, int R2, int BT, int NW, int SP0, int SP1, int NSTAGE = 2, bool INPLACE = false>
 static cudaError_t run_doppler(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
@@ -562,7 +741,9 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     // (profiles/experiments/r1_k1_variants_sweep.log); the single-buffer BT = 16 shape stays
     case 256:  return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
     case 512:  return run_range<512, 16, 32, 16, 8, true, 256, 0>(p, adc, rs, n_frames, st);
-    case 1024: return run_range<1024, 32, 32, 16, 8, false, 512, 0>(p, adc, rs, n_frames, st);
+    // 1024 points: a 16-row tile needs 209 KB (one CTA per SM); 8 rows fit two CTAs per SM and measured 2.4 % faster
+    // (profiles/experiments/r1_cfg4_tile_sweep.log)
+    case 1024: return run_range<1024, 32, 32, 8, 8, false, 512, 0>(p, adc, rs, n_frames, st);
     default:   return cudaErrorInvalidValue;
     }
 }
@@ -573,31 +754,25 @@ cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube,
     case 64:   return run_doppler<64, 8, 8, 16, 4, 0, 0>(p, rs, cube, pmap, n_frames, st);
     case 128: {
         const int v = variant("MMW_K2_VARIANT");
+        // tile-shape experiments kept selectable for profiles/sweep_variants.py (results: profiles/experiments/)
+        // warp-private tiles (K2w) are slower at 128 points (4 rows x 8 lanes, two butterflies per thread): 0.222 vs 0.207 ms
+        if (v == 11 && !cube) return run_doppler_warp<128, 8, 16, 8, 256, 2>(p, rs, pmap, n_frames, st);
         if (v == 1) return run_doppler<128, 8, 16, 8, 4, 256, 128, 2>(p, rs, cube, pmap, n_frames, st);
-        if (v == 2) return run_doppler<128, 8, 16, 16, 4, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
-        if (v == 3) return run_doppler<128, 8, 16, 8, 4, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
-        if (v == 4) return run_doppler<128, 8, 16, 16, 8, 256, 128, 2>(p, rs, cube, pmap, n_frames, st);
-        if (v == 5) return run_doppler<128, 8, 16, 32, 8, 256, 128, 1>(p, rs, cube, pmap, n_frames, st);
         if (v == 6) return run_doppler<128, 8, 16, 16, 4, 256, 128, 3, true>(p, rs, cube, pmap, n_frames, st);
-        if (v == 7) return run_doppler<128, 8, 16, 16, 4, 256, 128, 4, true>(p, rs, cube, pmap, n_frames, st);
-        if (v == 8) return run_doppler<128, 8, 16, 16, 4, 256, 128, 2, true>(p, rs, cube, pmap, n_frames, st);
-        if (v == 9) return run_doppler<128, 8, 16, 16, 8, 256, 128, 3, true>(p, rs, cube, pmap, n_frames, st);
         return run_doppler<128, 8, 16, 16, 4, 256, 128>(p, rs, cube, pmap, n_frames, st);
     }
     case 256: {
         const int v = variant("MMW_K2_VARIANT");
         if (v == 1) return run_doppler<256, 16, 16, 8, 4, 512, 0, 2>(p, rs, cube, pmap, n_frames, st);
-        if (v == 2) return run_doppler<256, 16, 16, 16, 8, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
-        if (v == 3) return run_doppler<256, 16, 16, 8, 4, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
-        if (v == 4) return run_doppler<256, 16, 16, 16, 4, 512, 0, 2>(p, rs, cube, pmap, n_frames, st);
-        if (v == 5) return run_doppler<256, 16, 16, 16, 4, 512, 0, 1>(p, rs, cube, pmap, n_frames, st);
         if (v == 6) return run_doppler<256, 16, 16, 16, 8, 512, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
-        if (v == 7) return run_doppler<256, 16, 16, 16, 8, 512, 0, 2, true>(p, rs, cube, pmap, n_frames, st);
-        if (v == 8) return run_doppler<256, 16, 16, 16, 4, 512, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
-        if (v == 9) return run_doppler<256, 16, 16, 16, 8, 512, 0, 4, true>(p, rs, cube, pmap, n_frames, st);
+        if (v == 10 && !cube) return run_doppler_warp<256, 16, 16, 8, 512, 3>(p, rs, pmap, n_frames, st);
+        // fused mode (power map only): warp-private tiles, 0.156 vs 0.171 ms on cfg3 (profiles/experiments/r1_k2_warp_private.log)
+        if (v != 12 && !cube) return run_doppler_warp<256, 16, 16, 8, 512, 2>(p, rs, pmap, n_frames, st);
         return run_doppler<256, 16, 16, 16, 8, 512, 0>(p, rs, cube, pmap, n_frames, st);
     }
-    case 512:  return run_doppler<512, 16, 32, 16, 8, 1024, 0>(p, rs, cube, pmap, n_frames, st);
+    // 512 points: 8-row tiles, in place, three staging buffers = 103 KB, two CTAs per SM: 0.76 ms against 1.00 ms for the
+    // 16-row double-buffered shape (201 KB, one CTA per SM) on the cfg4 cube (profiles/experiments/r1_cfg4_tile_sweep.log)
+    case 512:  return run_doppler<512, 16, 32, 8, 8, 1024, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
     case 1024: return run_doppler<1024, 32, 32, 8, 8, 0, 0>(p, rs, cube, pmap, n_frames, st);
     default:   return cudaErrorInvalidValue;
     }

@@ -9,7 +9,7 @@ import torch  # noqa: E402
 import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
-SHAPES = {"cfg3": (512, 256, 12, 64), "cfg2": (256, 128, 4, 1024)}
+SHAPES = {"cfg3": (512, 256, 12, 64), "cfg2": (256, 128, 4, 1024), "cfg4": (1024, 512, 192, 4)}
 dev = torch.device("cuda", 0)
 nv1, nv2 = int(os.environ.get("NV1", 1)), int(os.environ.get("NV2", 6))
 for wl in (sys.argv[1:] or ["cfg3", "cfg2"]):
