@@ -212,14 +212,15 @@ class Env:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+        # keep stdout for the one JSON line: libraries (NCCL's version banner) write to fd 1 during init
+        sys.stdout.flush()
+        self.real_stdout = os.dup(1)
+        os.dup2(2, 1)
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", rank=self.rank, world_size=self.world, device_id=self.dev)
-        # keep stdout for the one JSON line: libraries (NCCL's version banner) write to fd 1 during init
-        self.real_stdout = os.dup(1)
-        os.dup2(2, 1)
         self.pkg = entry.load_package()
 
     def sync_all(self):
@@ -227,6 +228,14 @@ class Env:
         if self.world > 1:
             self.dist.barrier()
             self.torch.cuda.synchronize()
+
+    def all_ranks(self, x: float):
+        if self.world == 1:
+            return [x]
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        out = self.torch.empty(self.world, device=self.dev, dtype=self.torch.float64)
+        self.dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.cpu()]
 
     def max_over_ranks(self, x: float) -> float:
         if self.world == 1:
@@ -262,8 +271,8 @@ def run_chain(args, env):
     ctx.use_stream(stream.cuda_stream)
     dense_ptr, header_ptr = ctx.device_results()
     header_view = pkg.sharding.device_bytes_view(header_ptr, 16, dev)
-    # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel,
-    # software-pipelined one step behind the compute (sharding.DetectionGather)
+    # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel, on a
+    # side stream behind a snapshot of the block so that it overlaps the next step's kernels (sharding.DetectionGather)
     gather_records = min(F * ctx.max_det_per_frame, 32768)
     gather = pkg.sharding.DetectionGather(ctx, dev, gather_records) if world > 1 else None
 
@@ -290,7 +299,8 @@ def run_chain(args, env):
         e1.record(stream)
         env.sync_all()
         ms = e0.elapsed_time(e1)
-    ms = env.max_over_ranks(ms)
+    ms_by_rank = env.all_ranks(ms)
+    ms = max(ms_by_rank)
     frame_counts = ctx.read_counts(F)                       # true per-frame hit counts of this rank's last batch
     if world == 1:
         n_det_step, gather_overflow = int(header_view[:4].view(torch.int32).item()), 0
@@ -346,9 +356,10 @@ def run_chain(args, env):
                 "workload": f"{workload_text(args.workload)}, 2-D CA-CFAR (guard 2x2, train 8x4, alpha 15), "
                             f"{ctx.n_theta}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
                 "frames_per_gpu_per_step": F,
-                "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel, pipelined one step behind the compute (overflow={gather_overflow})"),
+                "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel on a side stream, overlapping the next step (overflow={gather_overflow})"),
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
                 "l2": f"inputs larger than L2: {F * 4 * N_adc / 1e6:.0f} MB int16 capture + {F * 8 * A * ctx.Sp * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
+                "ms_per_step_by_rank": [m / K for m in ms_by_rank],
                 "detections_per_step": n_det_step, "max_detections_in_one_frame": int(frame_counts.max()),
                 "max_det_per_frame": ctx.max_det_per_frame,
             },

@@ -75,7 +75,7 @@ def gather_detections(local_records, n_local, group=None):
 
 
 class DetectionGather:
-    """The exchange step of the sharded chain without a host round trip, pipelined one step behind the compute.
+    """The exchange step of the sharded chain: no host round trip, and off the compute stream.
 
     Every rank contributes a FIXED-size prefix of its contiguous result block ([32-byte header | ordered
     records], mmw_device_result_block) — `records_per_rank` records, a few hundred KB — so the sizes NCCL needs
@@ -84,15 +84,17 @@ class DetectionGather:
     kernel (mmw_merge_gathered), reading the true counts from the gathered headers on the device.  A rank that
     produced more than `records_per_rank` detections is truncated and the merged header's overflow word is set.
 
-    Pipelining: run() snapshots the result block (one small device copy on the compute stream), starts the
-    gather asynchronously (NCCL's own stream) and only then completes the PREVIOUS step's exchange (wait + merge),
-    so the transfer of step k overlaps the kernels of step k+1 instead of stalling the compute stream.
-    flush() completes the last one.  The context's stream must be torch's current stream."""
+    Overlap: run() snapshots the result block on the compute stream (one small device copy; the next batch
+    overwrites the block) and hands everything else — the NCCL gather and the merge kernel — to a side stream
+    that only depends on that snapshot, so the exchange of step k runs under the kernels of step k+1.  Send,
+    receive and merged buffers are double-buffered; flush() makes the compute stream wait for the last exchange.
+    The context's stream must be torch's current stream when run() is called."""
 
     def __init__(self, ctx, device, records_per_rank: int, group=None):
         import torch
         import torch.distributed as dist
 
+        self.torch = torch
         self.ctx, self.group = ctx, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         block, cap_bytes = ctx.device_result_block()
@@ -102,43 +104,50 @@ class DetectionGather:
         self.local = device_bytes_view(block, self.stride, device)
         self.send = [torch.empty(self.stride, dtype=torch.uint8, device=device) for _ in range(2)]
         self.merged_cap = self.world * records_per_rank
-        self.work = [None, None]
+        self.side = torch.cuda.Stream(device=device)
+        self.snap = [torch.cuda.Event() for _ in range(2)]       # snapshot k is in send[k]
+        self.done = [None, None]                                   # exchange that last used buffer pair k has finished
         self.step = 0
-        self.pending = None          # parity of the step whose gather has been started but not merged yet
         self.latest = None
         if self.rank == 0:
             self.gathered = [torch.empty((self.world, self.stride), dtype=torch.uint8, device=device) for _ in range(2)]
             self.slots = [list(g.unbind(0)) for g in self.gathered]
             self.merged = [torch.empty(32 + REC_BYTES * self.merged_cap, dtype=torch.uint8, device=device) for _ in range(2)]
 
-    def _complete(self, k):
-        self.work[k].wait()                                   # current stream waits for the NCCL stream
-        self.work[k] = None
-        if self.rank == 0:
-            self.ctx.merge_gathered(self.gathered[k], self.world, self.stride, self.merged[k], self.merged_cap)
-            self.latest = self.merged[k]
-
     def run(self):
-        """call after ctx.process_device(); returns the merged block of the PREVIOUS step on rank 0 (None on the first
-        call and on other ranks).  The block of this step becomes available after the next run() or flush()."""
+        """call after ctx.process_device() with the context's stream current.  Returns the merged block of this
+        step on rank 0 (None elsewhere); it is complete once flush() has been called or the side stream has been
+        waited for."""
         import torch.distributed as dist
 
+        torch = self.torch
         k = self.step & 1
         self.step += 1
-        self.send[k].copy_(self.local)                        # snapshot: the next batch overwrites the result block
+        compute = torch.cuda.current_stream()
+        if self.done[k] is not None:
+            compute.wait_event(self.done[k])                      # two steps old: never actually waits
+        self.send[k].copy_(self.local)
+        self.snap[k].record(compute)
         dst = dist.get_global_rank(self.group, 0) if self.group is not None else 0
-        self.work[k] = dist.gather(self.send[k], gather_list=self.slots[k] if self.rank == 0 else None, dst=dst,
-                                   group=self.group, async_op=True)
-        prev, self.pending = self.pending, k
-        if prev is not None:
-            self._complete(prev)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.snap[k])
+            dist.gather(self.send[k], gather_list=self.slots[k] if self.rank == 0 else None, dst=dst, group=self.group)
+            if self.rank == 0:
+                self.ctx.use_stream(self.side.cuda_stream)
+                self.ctx.merge_gathered(self.gathered[k], self.world, self.stride, self.merged[k], self.merged_cap)
+                self.ctx.use_stream(compute.cuda_stream)
+                self.latest = self.merged[k]
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.done[k] = ev
         return self.latest if self.rank == 0 else None
 
     def flush(self):
-        """completes the outstanding exchange; returns the merged block of the last step on rank 0"""
-        if self.pending is not None:
-            self._complete(self.pending)
-            self.pending = None
+        """the current stream waits for every exchange started so far; returns the last merged block on rank 0"""
+        cur = self.torch.cuda.current_stream()
+        for ev in self.done:
+            if ev is not None:
+                cur.wait_event(ev)
         return self.latest if self.rank == 0 else None
 
     def read(self, det_dtype):

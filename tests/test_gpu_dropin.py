@@ -43,3 +43,24 @@ def test_verification_harness_of_the_reference_main(pkg, orc, tmp_path):
                            env=dict(os.environ, MMW_LEGACY_QUIET="1"))
         assert r.returncode == 0, r.stdout + r.stderr
         assert "verified 39 frames, 0 mismatches" in r.stdout
+
+
+def test_cxx_host_program_against_the_c_abi(pkg, tmp_path):
+    """examples/b200_timing.cpp: plain C++ over include/mmw_radar.h (capture-file ingest + physical units), the program
+    INTEGRATION.md describes; its detection count must equal the in-memory path's."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "b200_timing"
+    r = subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-Wall", "-Werror", "-o", str(exe), os.path.join(root, "examples", "b200_timing.cpp"),
+                        "-I", os.path.join(root, "include"), pkg.api.library_path(),
+                        "-Wl,-rpath," + os.path.dirname(pkg.api.library_path())], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    S, C, A = 100, 128, 4
+    adc = pkg.synth.cube_batch(9, S, C, A, cfg=12, n_targets=3)
+    adc.tofile(tmp_path / "cap.bin")
+    with pkg.RadarContext(S, C, A, 9) as ctx:
+        want, _ = ctx.process_host(adc, 9)
+    r = subprocess.run([str(exe), str(tmp_path / "cap.bin"), str(S), str(C), str(A), "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"b200 detections {len(want)}," in r.stdout and "(9 frames" in r.stdout and "range " in r.stdout
+    r = subprocess.run([str(exe), str(tmp_path / "missing.bin"), str(S), str(C), str(A)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "unable to read the specified file" in r.stdout
