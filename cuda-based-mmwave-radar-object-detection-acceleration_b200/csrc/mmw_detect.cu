@@ -295,12 +295,14 @@ __global__ void __launch_bounds__(kListNT) list_kernel(PlanDev p, const uint32_t
 }
 
 // ---------------------------------------------------------------------------
-// K4b: one warp per chunk of up to kMeasG detections that share (frame, range bin)
+// K4b: detection records.  Chunks of up to kMeasG detections that share (frame, range bin) are measured together.
 // ---------------------------------------------------------------------------
 constexpr int kMeasNT = 256;
 constexpr int kMeasWarps = kMeasNT / 32;
 constexpr int kMeasG = 4;            // detections measured together (they share every range-spectrum row they read)
 constexpr int kMeasQ = 2;            // antennas whose rows are in flight together
+constexpr int kMeasWideA = 32;       // from this many antennas on, a whole CTA (not one warp) measures a chunk ...
+constexpr int kMeasWideG = 32;       // ... of up to this many detections (kMeasG at a time in registers, rows re-read from L1)
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -311,8 +313,197 @@ __device__ __forceinline__ float warp_sum(float v)
 
 // The list is ordered by (frame, range, doppler), so the hits a target leaves in neighbouring Doppler cells of one
 // range bin are consecutive.  In fused mode each of them needs one Doppler bin of the SAME A x C block of the range
-// spectrum; a run of equal range bin is cut into chunks of kMeasG detections, one warp per chunk, and the warp reads
-// every row once for all the detections of its chunk.
+// spectrum; a run of equal range bin is cut into chunks of kMeasG detections, and whoever measures a chunk reads every
+// row once for all its detections.
+struct MeasFrame {                   // cached frame lookup: list positions [fbeg, fend_raw) belong to frame f
+    int f;
+    uint32_t fbeg, fend_raw;
+};
+struct MeasChunk {
+    int f, r, ng;
+    uint32_t mykey;                  // lane j: key of the chunk's j-th detection (lanes >= ng: don't care)
+    __device__ __forceinline__ int doppler(int j) const { return (int)(__shfl_sync(0xffffffffu, mykey, min(j, ng - 1)) & 0xffffu); }
+};
+
+// Warp-collective.  Returns false if list position g0 is not the head of a chunk.  The neighbouring keys are read 32 at
+// a time, one per lane, so that finding the run costs one memory round trip instead of one per element.
+template <int G>
+__device__ __forceinline__ bool locate_chunk(const PlanDev &p, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ offsets,
+                                             int n_frames, uint32_t total, uint32_t g0, int lane, MeasFrame &fc, MeasChunk &ch)
+{
+    if (g0 < fc.fbeg || g0 >= fc.fend_raw) {
+        int lo = 0, hi = n_frames - 1;                            // largest f with offsets[f] <= g0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] <= g0) lo = mid; else hi = mid - 1;
+        }
+        fc.f = lo;
+        fc.fbeg = offsets[lo];
+        fc.fend_raw = offsets[lo + 1];
+    }
+    const uint32_t fbeg = fc.fbeg, fend = min(fc.fend_raw, total);
+    const uint32_t *kf = keys + (size_t)fc.f * p.max_det - fbeg;  // kf[g] = key of list position g
+    const int r = (int)(kf[g0] >> 16);
+    uint32_t back = 0;                                            // position of g0 inside its run of equal range bin
+    for (uint32_t base = g0;;) {                                  // 32 predecessors per round
+        const bool same = base >= fbeg + 1 + lane && (int)(kf[base - 1 - lane] >> 16) == r;
+        const uint32_t m = __ballot_sync(0xffffffffu, same);
+        const uint32_t n = m == 0xffffffffu ? 32u : (uint32_t)(__ffs(~m) - 1);
+        back += n;
+        if (n < 32u) break;
+        base -= 32u;
+    }
+    if (back % G != 0) return false;                              // every G-th detection of a run heads a chunk
+    const uint32_t mykey = g0 + lane < fend ? kf[g0 + lane] : 0xffffffffu;      // lane j: key of list position g0 + j
+    const uint32_t fm = __ballot_sync(0xffffffffu, g0 + lane < fend && (int)(mykey >> 16) == r);
+    ch.f = fc.f;
+    ch.r = r;
+    static_assert(G <= 32, "a chunk's keys live one per lane");
+    ch.ng = min(G, fm == 0xffffffffu ? 32 : __ffs(~fm) - 1);
+    ch.mykey = mykey;
+    return true;
+}
+
+// Warp-collective: antenna snapshots X[a] = Doppler bin d_j of antenna a at range bin r, for every detection j of the
+// chunk and the antennas a_first, a_first + kMeasQ, ... in steps of a_step, written to xw[j * A + a].
+// Cube mode copies them; fused mode re-derives them from the (already windowed) range spectrum: kMeasQ antennas x 256
+// chirps (kMeasQ * 8 independent 8-byte loads per lane) are pulled into registers before anything is consumed — this is
+// bound by memory latency, not by arithmetic — and every value then feeds kMeasG detections at a time; a longer chunk
+// re-reads the same few KB from L1.  The summation order per (antenna, detection) is fixed: lane-strided partial sums
+// in ascending chirp order, then the xor-butterfly.
+__device__ __forceinline__ void snapshot_antennas(const PlanDev &p, const float2 *__restrict__ rs, const float2 *__restrict__ cube,
+                                                  const MeasChunk &ch, int lane, int a_first, int a_step, float2 *xw)
+{
+    const int Sp = p.Sp, Cp = p.Cp, A = p.A, C = p.C;
+    const int f = ch.f, r = ch.r, ng = ch.ng;
+    if (cube != nullptr) {
+        for (int j = 0; j < ng; ++j) {
+            const int d = ch.doppler(j);
+            for (int e = lane;; e += 32) {                        // e-th antenna of this caller's share, one per lane
+                const int a0 = a_first + (e / kMeasQ) * a_step, a = a0 + e % kMeasQ;
+                if (a0 >= A) break;
+                if (a < A) xw[j * A + a] = cube[(((size_t)f * A + a) * Cp + d) * Sp + r];
+            }
+        }
+        return;
+    }
+    const float2 *src0 = rs + (((size_t)f * A) * Sp + r) * (size_t)C;
+    const size_t astride = (size_t)Sp * C;
+    for (int a0 = a_first; a0 < A; a0 += a_step) {
+        for (int jb = 0; jb < ng; jb += kMeasG) {
+            int dj[kMeasG];
+#pragma unroll
+            for (int j = 0; j < kMeasG; ++j) dj[j] = ch.doppler(jb + j);
+            const int nj = min(kMeasG, ng - jb);
+            float sx[kMeasG][kMeasQ], sy[kMeasG][kMeasQ];
+#pragma unroll
+            for (int j = 0; j < kMeasG; ++j)
+#pragma unroll
+                for (int q = 0; q < kMeasQ; ++q) sx[j][q] = sy[j][q] = 0.f;
+            for (int cc0 = 0; cc0 < C; cc0 += 256) {
+                float2 v[kMeasQ][8];
+#pragma unroll
+                for (int q = 0; q < kMeasQ; ++q) {
+                    const float2 *sa = src0 + (size_t)min(a0 + q, A - 1) * astride;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = cc0 + lane + 32 * i;
+                        v[q][i] = c < C ? sa[c] : make_float2(0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kMeasG; ++j) {
+                    if (j < nj) {
+                        const int d = dj[j];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int c = cc0 + lane + 32 * i;
+                            const float2 w = p.tw_d[(c * d) & (Cp - 1)];
+#pragma unroll
+                            for (int q = 0; q < kMeasQ; ++q) {
+                                sx[j][q] += v[q][i].x * w.x - v[q][i].y * w.y;
+                                sy[j][q] += v[q][i].x * w.y + v[q][i].y * w.x;
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kMeasG; ++j)
+#pragma unroll
+                for (int q = 0; q < kMeasQ; ++q)
+                    if (j < nj) {                                 // warp-uniform
+                        const float tx = warp_sum(sx[j][q]), ty = warp_sum(sy[j][q]);
+                        if (lane == 0 && a0 + q < A) xw[(jb + j) * A + a0 + q] = make_float2(tx, ty);
+                    }
+        }
+    }
+}
+
+// Warp-collective: strict 3x3 maximum among detected cells (Doppler wraps, range clamps; ties -> lowest (r,d))
+__device__ __forceinline__ bool group_peak(const PlanDev &p, const float *__restrict__ pf, const uint32_t *__restrict__ mf, int r, int d,
+                                           float pw, int lane)
+{
+    const int Sp = p.Sp, Cp = p.Cp;
+    const uint32_t key = ((uint32_t)r << 16) | (uint32_t)d;
+    bool worse = false;
+    if (lane < 9 && lane != 4) {
+        const int rr = r + lane / 3 - 1;
+        const int dd = (d + lane % 3 - 1 + Cp) & (Cp - 1);
+        if (rr >= 0 && rr < Sp) {
+            const uint32_t w = mf[(size_t)(dd >> 5) * Sp + rr];
+            if ((w >> (dd & 31)) & 1u) {
+                const float pn = pf[(size_t)dd * Sp + rr];
+                const uint32_t kn = ((uint32_t)rr << 16) | (uint32_t)dd;
+                worse = (pn > pw) || (pn == pw && kn < key);
+            }
+        }
+    }
+    return __ballot_sync(0xffffffffu, worse) == 0u;
+}
+
+__device__ __forceinline__ void angle_bin_power(const float2 *xj, const float2 *twa, int A, int n_theta, int k, float &best, int &bestk)
+{
+    float yx = 0.f, yy = 0.f;
+    for (int a = 0; a < A; ++a) {
+        const float2 v = xj[a];
+        const float2 w = twa[(k * a) & (n_theta - 1)];
+        yx += v.x * w.x - v.y * w.y;
+        yy += v.x * w.y + v.y * w.x;
+    }
+    const float m = yx * yx + yy * yy;
+    if (m > best || (m == best && k < bestk)) { best = m; bestk = k; }      // strict >, first wins
+}
+
+__device__ __forceinline__ void warp_argmax(float &best, int &bestk)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+        if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+    }
+}
+
+__device__ __forceinline__ void write_record(const PlanDev &p, mmw_detection *__restrict__ dense, uint32_t g, int f, int r, int d, float pw,
+                                             float noise, int bestk, bool is_peak)
+{
+    const int kw = bestk < p.n_theta / 2 ? bestk : bestk - p.n_theta;
+    float sn = (float)kw * p.lambda_over_d / (float)p.n_theta;
+    sn = fminf(1.f, fmaxf(-1.f, sn));
+    mmw_detection o;
+    o.frame = (uint32_t)f + p.frame_offset;
+    o.range_bin = (uint16_t)r;
+    o.doppler_bin = (uint16_t)d;
+    o.power = pw;
+    o.noise = noise;
+    o.angle_bin = (int16_t)kw;
+    o.flags = is_peak ? MMW_FLAG_PEAK : 0;
+    o.angle_rad = asinf(sn);
+    dense[g] = o;
+}
+
+// narrow form (A < kMeasWideA): one warp per chunk
 __global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float2 *__restrict__ rs, const float2 *__restrict__ cube,
                                                           const float *__restrict__ pmap, const float *__restrict__ noise_map,
                                                           const uint32_t *__restrict__ mask, const uint32_t *__restrict__ keys,
@@ -324,7 +515,7 @@ __global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float
     float2 *xs = twa + p.n_theta;                                   // [warps][kMeasG][A]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int Sp = p.Sp, Cp = p.Cp, A = p.A, C = p.C;
+    const int Sp = p.Sp, Cp = p.Cp, A = p.A;
     for (int i = tid; i < p.n_theta; i += kMeasNT) twa[i] = p.tw_a[i];
     __syncthreads();
 
@@ -334,178 +525,87 @@ __global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float
     // irregularly through the list, and a static assignment leaves most warps of an SM without one.  Long lists are
     // handed out in blocks of consecutive positions, which share the frame lookup and their neighbours' keys.
     const uint32_t blk = min(8u, max(1u, total / (uint32_t)(gridDim.x * kMeasWarps)));
-    int f = 0;
-    uint32_t fbeg = 0, fend_raw = 0;                                // cached frame: list positions [fbeg, fend_raw)
+    MeasFrame fc = {0, 0u, 0u};
     for (;;) {
         uint32_t gblk = 0;
         if (lane == 0) gblk = atomicAdd(cursor, blk);
         gblk = __shfl_sync(0xffffffffu, gblk, 0);
         if (gblk >= total) break;
         for (uint32_t g0 = gblk; g0 < min(gblk + blk, total); ++g0) {
-            if (g0 < fbeg || g0 >= fend_raw) {
-                // frame of detection g0: largest f with offsets[f] <= g0
-                int lo = 0, hi = n_frames - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (offsets[mid] <= g0) lo = mid; else hi = mid - 1;
-                }
-                f = lo;
-                fbeg = offsets[f];
-                fend_raw = offsets[f + 1];
+            MeasChunk ch;
+            if (!locate_chunk<kMeasG>(p, keys, offsets, n_frames, total, g0, lane, fc, ch)) continue;
+            const float *pf = pmap + (size_t)ch.f * Cp * Sp;
+            const uint32_t *mf = mask + (size_t)ch.f * (Cp / 32) * Sp;
+            snapshot_antennas(p, rs, cube, ch, lane, 0, kMeasQ, xw);
+            __syncwarp();
+            for (int j = 0; j < ch.ng; ++j) {
+                const int d = ch.doppler(j);
+                const float pw = pf[(size_t)d * Sp + ch.r];
+                const float noise = noise_map[((size_t)ch.f * Cp + d) * Sp + ch.r];
+                const bool is_peak = group_peak(p, pf, mf, ch.r, d, pw, lane);
+                float best = -1.f;
+                int bestk = 0;
+                for (int k = lane; k < p.n_theta; k += 32) angle_bin_power(xw + j * A, twa, A, p.n_theta, k, best, bestk);
+                warp_argmax(best, bestk);
+                if (lane == 0) write_record(p, dense, g0 + j, ch.f, ch.r, d, pw, noise, bestk, is_peak);
             }
-            const uint32_t fend = min(fend_raw, total);
-            const uint32_t *kf = keys + (size_t)f * p.max_det - fbeg;  // kf[g] = key of list position g
-            const uint32_t key0 = kf[g0];
-            const int r = key0 >> 16;
-            // position of g0 inside its run of equal range bin; every kMeasG-th detection of a run heads a chunk and its
-            // warp measures the chunk (the others return: their chunk head does them).  The neighbouring keys are read 32
-            // at a time, one per lane, so that finding the run costs one memory round trip instead of one per element.
-            uint32_t back = 0;
-            for (uint32_t base = g0;;) {                              // 32 predecessors per round
-                const bool same = base >= fbeg + 1 + lane && (int)(kf[base - 1 - lane] >> 16) == r;
-                const uint32_t m = __ballot_sync(0xffffffffu, same);
-                const uint32_t n = m == 0xffffffffu ? 32u : (uint32_t)(__ffs(~m) - 1);
-                back += n;
-                if (n < 32u) break;
-                base -= 32u;
+            __syncwarp();
+        }
+    }
+}
+
+// wide form (A >= kMeasWideA, e.g. the 192-antenna imaging cube: 786 KB of range spectrum per range bin): a whole CTA
+// measures a chunk of up to kMeasWideG detections — the warps split the antennas of the snapshot and the bins of the
+// angle spectrum — so the serial chain of memory round trips per chunk is eight times shorter and a long run of hits in
+// one range bin pulls its rows from HBM once.
+__global__ void __launch_bounds__(kMeasNT) measure_wide_kernel(PlanDev p, const float2 *__restrict__ rs, const float2 *__restrict__ cube,
+                                                               const float *__restrict__ pmap, const float *__restrict__ noise_map,
+                                                               const uint32_t *__restrict__ mask, const uint32_t *__restrict__ keys,
+                                                               const uint32_t *__restrict__ offsets, mmw_detection *__restrict__ dense,
+                                                               unsigned int *__restrict__ cursor, int n_frames, int dense_cap)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2 *twa = reinterpret_cast<float2 *>(smem);                 // [n_theta]
+    float2 *xs = twa + p.n_theta;                                   // [kMeasWideG][A], shared by the CTA
+    __shared__ uint32_t s_g0;
+    __shared__ float s_best[kMeasWarps];
+    __shared__ int s_bestk[kMeasWarps];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Sp = p.Sp, Cp = p.Cp, A = p.A;
+    for (int i = tid; i < p.n_theta; i += kMeasNT) twa[i] = p.tw_a[i];
+    const uint32_t total = min(offsets[n_frames], (uint32_t)dense_cap);
+    MeasFrame fc = {0, 0u, 0u};
+    for (;;) {
+        __syncthreads();                                             // s_g0 / xs / s_best free again (and twa loaded)
+        if (tid == 0) s_g0 = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const uint32_t g0 = s_g0;
+        if (g0 >= total) break;
+        MeasChunk ch;                                                // every warp derives the same chunk (uniform control flow)
+        if (!locate_chunk<kMeasWideG>(p, keys, offsets, n_frames, total, g0, lane, fc, ch)) continue;
+        const float *pf = pmap + (size_t)ch.f * Cp * Sp;
+        const uint32_t *mf = mask + (size_t)ch.f * (Cp / 32) * Sp;
+        snapshot_antennas(p, rs, cube, ch, lane, warp * kMeasQ, kMeasWarps * kMeasQ, xs);
+        __syncthreads();
+        for (int j = 0; j < ch.ng; ++j) {
+            float best = -1.f;
+            int bestk = 0;
+            for (int k = tid; k < p.n_theta; k += kMeasNT) angle_bin_power(xs + j * A, twa, A, p.n_theta, k, best, bestk);
+            warp_argmax(best, bestk);
+            if (lane == 0) { s_best[warp] = best; s_bestk[warp] = bestk; }
+            __syncthreads();
+            if (warp == 0) {
+                best = lane < kMeasWarps ? s_best[lane] : -1.f;
+                bestk = lane < kMeasWarps ? s_bestk[lane] : 0x7fffffff;
+                warp_argmax(best, bestk);
+                const int d = ch.doppler(j);
+                const float pw = pf[(size_t)d * Sp + ch.r];
+                const float noise = noise_map[((size_t)ch.f * Cp + d) * Sp + ch.r];
+                const bool is_peak = group_peak(p, pf, mf, ch.r, d, pw, lane);
+                if (lane == 0) write_record(p, dense, g0 + j, ch.f, ch.r, d, pw, noise, bestk, is_peak);
             }
-            if (back % kMeasG != 0) continue;
-            const uint32_t mykey = g0 + lane < fend ? kf[g0 + lane] : 0xffffffffu;      // lane j: key of list position g0 + j
-            const uint32_t fm = __ballot_sync(0xffffffffu, g0 + lane < fend && (int)(mykey >> 16) == r);
-            const int ng = min(kMeasG, fm == 0xffffffffu ? 32 : __ffs(~fm) - 1);
-
-            const float *pf = pmap + (size_t)f * Cp * Sp;
-            const uint32_t *mf = mask + (size_t)f * (Cp / 32) * Sp;
-
-            {
-                const uint32_t gb = g0;
-                int dj[kMeasG];
-#pragma unroll
-                for (int j = 0; j < kMeasG; ++j) dj[j] = (int)(__shfl_sync(0xffffffffu, mykey, min(j, ng - 1)) & 0xffffu);
-
-                // antenna snapshots at (r, d_j)
-                if (cube != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < kMeasG; ++j)
-                        if (j < ng)
-                            for (int a = lane; a < A; a += 32) xw[j * A + a] = cube[(((size_t)f * A + a) * Cp + dj[j]) * Sp + r];
-                } else {
-                    // fused mode: Doppler bins d_j of every antenna straight from the (already windowed) range spectrum.
-                    // kMeasQ antennas x 256 chirps (kMeasQ * 8 independent 8-byte loads per lane) are pulled into registers
-                    // before anything is consumed — the kernel is bound by memory latency, not by arithmetic — and every
-                    // value then feeds all the chunk's detections.  The summation order per (antenna, detection) is fixed:
-                    // lane-strided partial sums in ascending chirp order, then the xor-butterfly over lanes.
-                    const float2 *src0 = rs + (((size_t)f * A) * Sp + r) * (size_t)C;
-                    const size_t astride = (size_t)Sp * C;
-                    for (int a0 = 0; a0 < A; a0 += kMeasQ) {
-                        float sx[kMeasG][kMeasQ], sy[kMeasG][kMeasQ];
-#pragma unroll
-                        for (int j = 0; j < kMeasG; ++j)
-#pragma unroll
-                            for (int q = 0; q < kMeasQ; ++q) sx[j][q] = sy[j][q] = 0.f;
-                        for (int cc0 = 0; cc0 < C; cc0 += 256) {
-                            float2 v[kMeasQ][8];
-#pragma unroll
-                            for (int q = 0; q < kMeasQ; ++q) {
-                                const float2 *sa = src0 + (size_t)min(a0 + q, A - 1) * astride;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int c = cc0 + lane + 32 * i;
-                                    v[q][i] = c < C ? sa[c] : make_float2(0.f, 0.f);
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < kMeasG; ++j) {
-                                if (j < ng) {
-                                    const int d = dj[j];
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const int c = cc0 + lane + 32 * i;
-                                        const float2 w = p.tw_d[(c * d) & (Cp - 1)];
-#pragma unroll
-                                        for (int q = 0; q < kMeasQ; ++q) {
-                                            sx[j][q] += v[q][i].x * w.x - v[q][i].y * w.y;
-                                            sy[j][q] += v[q][i].x * w.y + v[q][i].y * w.x;
-                                        }
-                                    }
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < kMeasG; ++j)
-#pragma unroll
-                            for (int q = 0; q < kMeasQ; ++q) {
-                                const float tx = warp_sum(sx[j][q]), ty = warp_sum(sy[j][q]);
-                                if (lane == 0 && j < ng && a0 + q < A) xw[j * A + a0 + q] = make_float2(tx, ty);
-                            }
-                    }
-                }
-                __syncwarp();
-
-#pragma unroll
-                for (int j = 0; j < kMeasG; ++j) {
-                    if (j >= ng) break;
-                    const uint32_t g = gb + j;
-                    const int d = dj[j];
-                    const uint32_t key = ((uint32_t)r << 16) | (uint32_t)d;
-                    const float pw = pf[(size_t)d * Sp + r];
-                    const float noise = noise_map[((size_t)f * Cp + d) * Sp + r];
-
-                    // 3x3 grouping among detected cells (Doppler wraps, range clamps; ties -> lowest (r,d))
-                    bool worse = false;
-                    if (lane < 9 && lane != 4) {
-                        const int rr = r + lane / 3 - 1;
-                        const int dd = (d + lane % 3 - 1 + Cp) & (Cp - 1);
-                        if (rr >= 0 && rr < Sp) {
-                            const uint32_t w = mf[(size_t)(dd >> 5) * Sp + rr];
-                            if ((w >> (dd & 31)) & 1u) {
-                                const float pn = pf[(size_t)dd * Sp + rr];
-                                const uint32_t kn = ((uint32_t)rr << 16) | (uint32_t)dd;
-                                worse = (pn > pw) || (pn == pw && kn < key);
-                            }
-                        }
-                    }
-                    const bool is_peak = __ballot_sync(0xffffffffu, worse) == 0u;
-
-                    // angle spectrum arg-max (strict >, first wins)
-                    const float2 *xj = xw + j * A;
-                    float best = -1.f;
-                    int bestk = 0;
-                    for (int k = lane; k < p.n_theta; k += 32) {
-                        float yx = 0.f, yy = 0.f;
-                        for (int a = 0; a < A; ++a) {
-                            const float2 v = xj[a];
-                            const float2 w = twa[(k * a) & (p.n_theta - 1)];
-                            yx += v.x * w.x - v.y * w.y;
-                            yy += v.x * w.y + v.y * w.x;
-                        }
-                        const float m = yx * yx + yy * yy;
-                        if (m > best) { best = m; bestk = k; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                        const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
-                        if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
-                    }
-                    if (lane == 0) {
-                        const int kw = bestk < p.n_theta / 2 ? bestk : bestk - p.n_theta;
-                        float sn = (float)kw * p.lambda_over_d / (float)p.n_theta;
-                        sn = fminf(1.f, fmaxf(-1.f, sn));
-                        mmw_detection o;
-                        o.frame = (uint32_t)f + p.frame_offset;
-                        o.range_bin = (uint16_t)r;
-                        o.doppler_bin = (uint16_t)d;
-                        o.power = pw;
-                        o.noise = noise;
-                        o.angle_bin = (int16_t)kw;
-                        o.flags = is_peak ? MMW_FLAG_PEAK : 0;
-                        o.angle_rad = asinf(sn);
-                        dense[g] = o;
-                    }
-                }
-                __syncwarp();
-            }
+            __syncthreads();
         }
     }
 }
@@ -589,15 +689,21 @@ cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames
     list_kernel<<<n_frames, kListNT, 0, st>>>(p, b.mask, b.keys, b.counts, b.offsets, b.header, b.ticket, n_frames, dense_cap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int bytes = p.n_theta * 8 + kMeasWarps * kMeasG * p.A * 8;
-    static int configured = 0;
-    if (bytes > configured) {
-        e = cudaFuncSetAttribute(measure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    const bool wide = p.A >= kMeasWideA;
+    const int bytes = p.n_theta * 8 + (wide ? kMeasWideG : kMeasWarps * kMeasG) * p.A * 8;
+    static int configured[2] = {0, 0};
+    if (bytes > configured[wide]) {
+        e = wide ? cudaFuncSetAttribute(measure_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+                 : cudaFuncSetAttribute(measure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        configured = bytes;
+        configured[wide] = bytes;
     }
-    measure_kernel<<<sm_count * 4, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask, b.keys,
-                                                         b.offsets, b.dense, b.ticket + 1, n_frames, dense_cap);
+    if (wide)
+        measure_wide_kernel<<<sm_count * 2, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask,
+                                                                  b.keys, b.offsets, b.dense, b.ticket + 1, n_frames, dense_cap);
+    else
+        measure_kernel<<<sm_count * 4, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask, b.keys,
+                                                             b.offsets, b.dense, b.ticket + 1, n_frames, dense_cap);
     return cudaGetLastError();
 }
 
