@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kListNT) list_kernel(PlanDev p, const uint32_t
     __shared__ uint32_t scan[kListNT / 32], tsum[kListNT / 32];
     __shared__ uint32_t total_s;
     __shared__ bool is_last;
+    extern __shared__ uint32_t ordered[];                     // the frame's mask words in (range, doppler-word) order
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int f = blockIdx.x;
@@ -210,12 +211,21 @@ __global__ void __launch_bounds__(kListNT) list_kernel(PlanDev p, const uint32_t
     const uint32_t *mf = mask + (size_t)f * nwords;
     uint32_t *kf = keys + (size_t)f * p.max_det;
 
+    // the mask is stored [doppler word][range]; read it coalesced and transpose on the way into shared memory (one pad
+    // word per 32 keeps the strided writes off a single bank) so that the ordered walk below is local
+    for (int i = tid; i < nwords; i += kListNT) {
+        const int w = i / Sp, r = i - w * Sp;
+        const int o = r * wpr + w;
+        ordered[o + (o >> 5)] = mf[i];
+    }
+    __syncthreads();
+
     // thread t owns the contiguous run [i0, i1) of the (range, doppler-word) ordered word sequence
     const int wpt = (nwords + kListNT - 1) / kListNT;
     const int i0 = tid * wpt, i1 = min(nwords, i0 + wpt);
     uint32_t cnt = 0;
 #pragma unroll 8
-    for (int i = i0; i < i1; ++i) cnt += __popc(mf[(size_t)(i % wpr) * Sp + i / wpr]);
+    for (int i = i0; i < i1; ++i) cnt += __popc(ordered[i + (i >> 5)]);
     uint32_t incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(kListNT) list_kernel(PlanDev p, const uint32_t
     uint32_t pos = scan[warp] + incl - cnt;
     if (cnt) {
         for (int i = i0; i < i1 && pos < (uint32_t)p.max_det; ++i) {
-            uint32_t w = mf[(size_t)(i % wpr) * Sp + i / wpr];
+            uint32_t w = ordered[i + (i >> 5)];
             const uint32_t r = i / wpr, dbase = (i % wpr) * 32;
             while (w && pos < (uint32_t)p.max_det) {
                 const int b = __ffs(w) - 1;
@@ -686,8 +696,17 @@ cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, flo
 
 cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st)
 {
-    list_kernel<<<n_frames, kListNT, 0, st>>>(p, b.mask, b.keys, b.counts, b.offsets, b.header, b.ticket, n_frames, dense_cap);
-    cudaError_t e = cudaGetLastError();
+    const int nwords = p.Sp * p.Cp / 32;
+    const int list_bytes = (nwords + nwords / 32 + 1) * 4;
+    static int list_configured = 0;
+    cudaError_t e;
+    if (list_bytes > list_configured) {
+        e = cudaFuncSetAttribute(list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, list_bytes);
+        if (e != cudaSuccess) return e;
+        list_configured = list_bytes;
+    }
+    list_kernel<<<n_frames, kListNT, list_bytes, st>>>(p, b.mask, b.keys, b.counts, b.offsets, b.header, b.ticket, n_frames, dense_cap);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const bool wide = p.A >= kMeasWideA;
     const int bytes = p.n_theta * 8 + (wide ? kMeasWideG : kMeasWarps * kMeasG) * p.A * 8;

@@ -12,7 +12,9 @@ NEAR = 1e-5         # |P - thr| <= NEAR * thr  -> cell is "at threshold", exclud
 
 # the last two exercise the 256-point angle FFT (A > 64: the cfg4 imaging array) and an odd antenna count
 SHAPES = [(64, 64, 2), (100, 128, 4), (128, 64, 12), (256, 128, 4), (512, 256, 12), (1024, 64, 2), (64, 1024, 1), (256, 512, 3),
-          (64, 64, 192), (128, 128, 65)]
+          (64, 64, 192), (128, 128, 65),
+          # ragged shapes: S a bare multiple of 4, C a bare multiple of 2, zero-padded to the next power of two on both axes
+          (68, 66, 3), (500, 130, 2)]
 
 
 def relmax(a, b):
@@ -152,6 +154,27 @@ def test_detection_list_overflow_is_ordered_and_counted(pkg, orc):
         assert cut.tobytes() == want.tobytes()                              # first 16 per frame, in order
         few, ov2 = ctx.process_host(adc, F, det_capacity=5)
         assert ov2 and few.tobytes() == want[:5].tobytes()
+
+
+def test_full_scale_int16_samples(pkg, orc):
+    """sign handling of the IIQQ unpack at the ends of the int16 range (-32768, 32767), alternating per sample"""
+    S, C, A, F = 64, 64, 2, 1
+    rng = np.random.default_rng(9)
+    adc = rng.choice(np.array([-32768, 32767, -1, 0, 1], np.int16), size=(F, 2 * S * C * A))
+    adc[0, :16] = [-32768, 32767, 32767, -32768, 32767, -32768, -32768, 32767] * 2
+    wr, wd = orc.hann_periodic(S), orc.hann_periodic(C)
+    ref = orc.process_frames(adc, F, S, C, A, wr, wd, want=("rs", "P"))
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        ctx.process_host(adc, F)
+        rs_ref = ref["rs"][0] * wd[None, None, :]
+        assert relmax(ctx.range_spectrum(0), rs_ref) < TOL
+        assert relmax(ctx.power_map(0), ref["P"][0]) < TOL
+        # rectangular windows: the first range bin of a constant full-scale row is exactly S * value
+        ctx.set_windows(np.ones(S, np.float32), np.ones(C, np.float32))
+        const = np.full((1, 2 * S * C * A), -32768, np.int16)
+        ctx.process_host(const, 1)
+        r0 = ctx.range_spectrum(0)[:, 0, :]
+        assert np.all(r0.real == -32768.0 * S) and np.all(r0.imag == -32768.0 * S)
 
 
 def test_empty_scene_and_zero_input(pkg):
