@@ -335,22 +335,26 @@ struct MeasChunk {
     __device__ __forceinline__ int doppler(int j) const { return (int)(__shfl_sync(0xffffffffu, mykey, min(j, ng - 1)) & 0xffffu); }
 };
 
+__device__ __forceinline__ void lookup_frame(const uint32_t *__restrict__ offsets, int n_frames, uint32_t g, MeasFrame &fc)
+{
+    if (g >= fc.fbeg && g < fc.fend_raw) return;
+    int lo = 0, hi = n_frames - 1;                                // largest f with offsets[f] <= g
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    fc.f = lo;
+    fc.fbeg = offsets[lo];
+    fc.fend_raw = offsets[lo + 1];
+}
+
 // Warp-collective.  Returns false if list position g0 is not the head of a chunk.  The neighbouring keys are read 32 at
 // a time, one per lane, so that finding the run costs one memory round trip instead of one per element.
 template <int G>
 __device__ __forceinline__ bool locate_chunk(const PlanDev &p, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ offsets,
                                              int n_frames, uint32_t total, uint32_t g0, int lane, MeasFrame &fc, MeasChunk &ch)
 {
-    if (g0 < fc.fbeg || g0 >= fc.fend_raw) {
-        int lo = 0, hi = n_frames - 1;                            // largest f with offsets[f] <= g0
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (offsets[mid] <= g0) lo = mid; else hi = mid - 1;
-        }
-        fc.f = lo;
-        fc.fbeg = offsets[lo];
-        fc.fend_raw = offsets[lo + 1];
-    }
+    lookup_frame(offsets, n_frames, g0, fc);
     const uint32_t fbeg = fc.fbeg, fend = min(fc.fend_raw, total);
     const uint32_t *kf = keys + (size_t)fc.f * p.max_det - fbeg;  // kf[g] = key of list position g
     const int r = (int)(kf[g0] >> 16);
@@ -513,7 +517,56 @@ __device__ __forceinline__ void write_record(const PlanDev &p, mmw_detection *__
     dense[g] = o;
 }
 
-// narrow form (A < kMeasWideA): one warp per chunk
+// Warp-collective: records of all (<= kMeasG <= 4) detections of a chunk.  Lane l looks at neighbour l % 8 of detection
+// l / 8, so the grouping test of the whole chunk costs two memory round trips (mask words, then the neighbours' powers)
+// instead of two per detection; the angle spectra come from the snapshots in shared memory.
+__device__ __forceinline__ void emit_chunk(const PlanDev &p, const float *__restrict__ pf, const uint32_t *__restrict__ mf,
+                                           const float *__restrict__ noise_map, const MeasChunk &ch, int lane, const float2 *xw,
+                                           const float2 *twa, mmw_detection *__restrict__ dense, uint32_t g0)
+{
+    static_assert(kMeasG * 8 <= 32, "one lane per (detection, neighbour)");
+    const int Sp = p.Sp, Cp = p.Cp, A = p.A;
+    const int j = lane >> 3, nb = lane & 7;
+    const bool active = j < ch.ng;
+    const int r = ch.r;
+    const int d = (int)(__shfl_sync(0xffffffffu, ch.mykey, min(j, ch.ng - 1)) & 0xffffu);
+    const uint32_t key = ((uint32_t)r << 16) | (uint32_t)d;
+    const float pw = active ? pf[(size_t)d * Sp + r] : 0.f;
+    const float noise = (active && nb == 0) ? noise_map[((size_t)ch.f * Cp + d) * Sp + r] : 0.f;
+    // 3x3 grouping among detected cells (Doppler wraps, range clamps; ties -> lowest (r,d)); nb skips the centre
+    const int cell = nb < 4 ? nb : nb + 1;
+    const int rr = r + cell / 3 - 1;
+    const int dd = (d + cell % 3 - 1 + Cp) & (Cp - 1);
+    bool worse = false;
+    if (active && rr >= 0 && rr < Sp) {
+        const uint32_t w = mf[(size_t)(dd >> 5) * Sp + rr];
+        if ((w >> (dd & 31)) & 1u) {
+            const float pn = pf[(size_t)dd * Sp + rr];
+            const uint32_t kn = ((uint32_t)rr << 16) | (uint32_t)dd;
+            worse = (pn > pw) || (pn == pw && kn < key);
+        }
+    }
+    const uint32_t wm = __ballot_sync(0xffffffffu, worse);
+    const bool is_peak = ((wm >> (8 * j)) & 0xffu) == 0u;
+    int my_bestk = 0;
+    for (int jj = 0; jj < ch.ng; ++jj) {
+        float best = -1.f;
+        int bestk = 0;
+        for (int k = lane; k < p.n_theta; k += 32) angle_bin_power(xw + jj * A, twa, A, p.n_theta, k, best, bestk);
+        warp_argmax(best, bestk);
+        if (j == jj) my_bestk = bestk;
+    }
+    if (active && nb == 0) write_record(p, dense, g0 + j, ch.f, r, d, pw, noise, my_bestk, is_peak);
+}
+
+// narrow form (A < kMeasWideA): one warp per chunk.
+// List positions are handed out from a global cursor (reset by list_kernel) in blocks of up to kMeasBlk consecutive
+// positions: chunk heads are scattered irregularly through the list, so a static assignment leaves most warps of an SM
+// without one, and the kernel is bound by memory round trips, so everything that can be is done for a whole block at
+// once — one lane-parallel read brings the block's keys, shuffles find every chunk head in it, and only the per-chunk
+// measurements remain serial.
+constexpr int kMeasBlk = 32 - kMeasG;                             // + kMeasG - 1 keys of look-ahead fit the 32 lanes
+
 __global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float2 *__restrict__ rs, const float2 *__restrict__ cube,
                                                           const float *__restrict__ pmap, const float *__restrict__ noise_map,
                                                           const uint32_t *__restrict__ mask, const uint32_t *__restrict__ keys,
@@ -531,35 +584,56 @@ __global__ void __launch_bounds__(kMeasNT) measure_kernel(PlanDev p, const float
 
     const uint32_t total = min(offsets[n_frames], (uint32_t)dense_cap);
     float2 *xw = xs + warp * (kMeasG * A);
-    // list positions are handed out from a global cursor (reset by list_kernel): chunk heads are scattered
-    // irregularly through the list, and a static assignment leaves most warps of an SM without one.  Long lists are
-    // handed out in blocks of consecutive positions, which share the frame lookup and their neighbours' keys.
-    const uint32_t blk = min(8u, max(1u, total / (uint32_t)(gridDim.x * kMeasWarps)));
+    const uint32_t blk = min((uint32_t)kMeasBlk, max(1u, total / (uint32_t)(gridDim.x * kMeasWarps)));
     MeasFrame fc = {0, 0u, 0u};
     for (;;) {
         uint32_t gblk = 0;
         if (lane == 0) gblk = atomicAdd(cursor, blk);
         gblk = __shfl_sync(0xffffffffu, gblk, 0);
         if (gblk >= total) break;
-        for (uint32_t g0 = gblk; g0 < min(gblk + blk, total); ++g0) {
-            MeasChunk ch;
-            if (!locate_chunk<kMeasG>(p, keys, offsets, n_frames, total, g0, lane, fc, ch)) continue;
-            const float *pf = pmap + (size_t)ch.f * Cp * Sp;
-            const uint32_t *mf = mask + (size_t)ch.f * (Cp / 32) * Sp;
-            snapshot_antennas(p, rs, cube, ch, lane, 0, kMeasQ, xw);
-            __syncwarp();
-            for (int j = 0; j < ch.ng; ++j) {
-                const int d = ch.doppler(j);
-                const float pw = pf[(size_t)d * Sp + ch.r];
-                const float noise = noise_map[((size_t)ch.f * Cp + d) * Sp + ch.r];
-                const bool is_peak = group_peak(p, pf, mf, ch.r, d, pw, lane);
-                float best = -1.f;
-                int bestk = 0;
-                for (int k = lane; k < p.n_theta; k += 32) angle_bin_power(xw + j * A, twa, A, p.n_theta, k, best, bestk);
-                warp_argmax(best, bestk);
-                if (lane == 0) write_record(p, dense, g0 + j, ch.f, ch.r, d, pw, noise, bestk, is_peak);
+        const uint32_t gblk_end = min(gblk + blk, total);
+        for (uint32_t g = gblk; g < gblk_end;) {                     // one segment per frame the block touches
+            lookup_frame(offsets, n_frames, g, fc);
+            const uint32_t fbeg = fc.fbeg, fend = min(fc.fend_raw, total);
+            const uint32_t seg_end = min(gblk_end, fend);
+            const uint32_t *kf = keys + (size_t)fc.f * p.max_det - fbeg;      // kf[q] = key of list position q
+            // keys of positions g .. g+31 (the segment and its look-ahead), and the predecessors of g, in one round trip
+            const bool valid = g + lane < fend;
+            const uint32_t mykey = valid ? kf[g + lane] : 0xffffffffu;
+            const int myr = (int)(mykey >> 16);
+            const int r_first = __shfl_sync(0xffffffffu, myr, 0);
+            uint32_t back = 0;                                        // how far the run of position g reaches back
+            for (uint32_t base = g;;) {
+                const bool same = base >= fbeg + 1 + lane && (int)(kf[base - 1 - lane] >> 16) == r_first;
+                const uint32_t m = __ballot_sync(0xffffffffu, same);
+                const uint32_t n = m == 0xffffffffu ? 32u : (uint32_t)(__ffs(~m) - 1);
+                back += n;
+                if (n < 32u) break;
+                base -= 32u;
             }
-            __syncwarp();
+            // index of every position inside its run of equal range bin -> chunk heads (every kMeasG-th)
+            const int prev_r = __shfl_up_sync(0xffffffffu, myr, 1);
+            const uint32_t starts = __ballot_sync(0xffffffffu, lane > 0 && valid && myr != prev_r);
+            const uint32_t below = starts & (0xffffffffu >> (31 - lane));         // run starts at lanes <= mine
+            const uint32_t idx = below ? (uint32_t)(lane - (31 - __clz(below))) : back + lane;
+            uint32_t heads = __ballot_sync(0xffffffffu, g + lane < seg_end && idx % kMeasG == 0);
+            const float *pf = pmap + (size_t)fc.f * Cp * Sp;
+            const uint32_t *mf = mask + (size_t)fc.f * (Cp / 32) * Sp;
+            while (heads) {
+                const int h = __ffs(heads) - 1;
+                heads &= heads - 1;
+                MeasChunk ch;
+                ch.f = fc.f;
+                ch.r = __shfl_sync(0xffffffffu, myr, h);
+                const uint32_t same = __ballot_sync(0xffffffffu, valid && myr == ch.r) >> h;      // bit j: position h + j
+                ch.ng = min(kMeasG, same == 0xffffffffu ? 32 : __ffs(~same) - 1);
+                ch.mykey = __shfl_sync(0xffffffffu, mykey, (h + lane) & 31);                       // lane j: position h + j
+                snapshot_antennas(p, rs, cube, ch, lane, 0, kMeasQ, xw);
+                __syncwarp();
+                emit_chunk(p, pf, mf, noise_map, ch, lane, xw, twa, dense, g + h);
+                __syncwarp();
+            }
+            g = seg_end;
         }
     }
 }
