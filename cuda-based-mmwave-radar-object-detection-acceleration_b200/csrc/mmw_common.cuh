@@ -116,6 +116,8 @@ cudaError_t launch_export_cube(const PlanDev &p, const float2 *cube_frame, float
 cudaError_t launch_export_pmap(const PlanDev &p, const float *pmap_frame, float *out, cudaStream_t st);
 cudaError_t launch_export_mask(const PlanDev &p, const uint32_t *mask_frame, uint8_t *out, cudaStream_t st);
 bool plan_supported(int Sp, int Cp, const char **why);
+constexpr int kMaxDevices = 64;
+int current_device();       // ordinal of the calling thread's current device, clamped to [0, kMaxDevices)
 void plan_radices(int n, int *r1, int *r2);
 
 // legacy single-frame path (mmw_legacy.cu)

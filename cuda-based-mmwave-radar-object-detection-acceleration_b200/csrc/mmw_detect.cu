@@ -753,7 +753,8 @@ cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, flo
 {
     const int bytes = cfar_smem_bytes(p);
     const bool fixed = p.guard_r == 2 && p.guard_d == 2 && p.win_r_half == 10 && p.win_d_half == 6;
-    static int configured[2] = {0, 0};
+    static int configured_dev[kMaxDevices][2] = {{0}};
+    int *configured = configured_dev[current_device()];
     if (bytes > configured[fixed]) {
         cudaError_t e = fixed ? cudaFuncSetAttribute(cfar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
                               : cudaFuncSetAttribute(cfar_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -772,7 +773,8 @@ cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames
 {
     const int nwords = p.Sp * p.Cp / 32;
     const int list_bytes = (nwords + nwords / 32 + 1) * 4;
-    static int list_configured = 0;
+    static int list_configured_dev[kMaxDevices] = {0};
+    int &list_configured = list_configured_dev[current_device()];
     cudaError_t e;
     if (list_bytes > list_configured) {
         e = cudaFuncSetAttribute(list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, list_bytes);
@@ -784,7 +786,8 @@ cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames
     if (e != cudaSuccess) return e;
     const bool wide = p.A >= kMeasWideA;
     const int bytes = p.n_theta * 8 + (wide ? kMeasWideG : kMeasWarps * kMeasG) * p.A * 8;
-    static int configured[2] = {0, 0};
+    static int configured_dev[kMaxDevices][2] = {{0}};
+    int *configured = configured_dev[current_device()];
     if (bytes > configured[wide]) {
         e = wide ? cudaFuncSetAttribute(measure_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
                  : cudaFuncSetAttribute(measure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

@@ -602,16 +602,24 @@ __global__ void export_mask_kernel(const uint32_t *__restrict__ in, uint8_t *__r
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-static int g_sm_count = 0;
+// Function attributes (opt-in shared memory) and occupancy are per device: a process may hold contexts on several GPUs
+// (mmw_config.device), so everything cached about a kernel is cached per device ordinal.
+int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
 static int sm_count()
 {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int count[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!count[dev]) {
+        cudaDeviceGetAttribute(&count[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (count[dev] <= 0) count[dev] = 148;
     }
-    return g_sm_count;
+    return count[dev];
 }
 
 template <typename K>
@@ -627,7 +635,8 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
 {
     auto k = range_fft_kernel<N, R1, R2, BT, NW, PAIR, PAD, CT, NSTAGE, BASE>;
     constexpr int bytes = RangeSmem<N, BT, NSTAGE>::kBytes;
-    static int per_sm = 0;
+    static int per_sm_dev[kMaxDevices] = {0};
+    int &per_sm = per_sm_dev[current_device()];
     if (!per_sm) {
         cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
         if (e != cudaSuccess) return e;
@@ -663,7 +672,8 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
 {
     auto k = doppler_fft_kernel<N, R1, R2, BT, NW, PAD, SPT, NSTAGE, INPLACE>;
     constexpr int bytes = DopplerSmem<N, BT, NSTAGE, INPLACE>::kBytes;
-    static int per_sm = 0;
+    static int per_sm_dev[kMaxDevices] = {0};
+    int &per_sm = per_sm_dev[current_device()];
     if (!per_sm) {
         cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
         if (e != cudaSuccess) return e;
@@ -681,7 +691,8 @@ static cudaError_t run_doppler_warp_t(const PlanDev &p, const float2 *rs, float 
     auto k = doppler_fft_warp_kernel<N, R1, R2, NW, PAD, SPT, NSTAGE>;
     using L = DopplerWarp<N, R1, R2>;
     constexpr int bytes = L::bytes(NW, NSTAGE);
-    static int per_sm = 0;
+    static int per_sm_dev[kMaxDevices] = {0};
+    int &per_sm = per_sm_dev[current_device()];
     if (!per_sm) {
         cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
         if (e != cudaSuccess) return e;

@@ -146,3 +146,23 @@ def test_merge_of_gathered_rank_blocks_equals_unsharded(pkg, batches):
     assert s[:32].view(np.uint32)[0] == 100 and s[:32].view(np.uint32)[3] == 1 and s[32:].tobytes() == whole[:100].tobytes()
     for c in ctxs:
         c.close()
+
+
+def test_contexts_on_two_devices_in_one_process(pkg, batches):
+    """mmw_config.device: one process may drive several GPUs (kernel attributes and occupancy are cached per device)"""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    S, C, A, F = FULL[0]
+    adc = batches[(S, C, A)]
+    with pkg.RadarContext(S, C, A, F, device=1) as c1:         # device 1 FIRST: nothing has been configured on it yet
+        d1, _ = c1.process_host(adc, F)
+        with pkg.RadarContext(S, C, A, F, device=0) as c0:
+            d0, _ = c0.process_host(adc, F)
+            half = F // 2
+            c1.set_frame_offset(half)
+            a, _ = c0.process_host(adc[:half], half)
+            b, _ = c1.process_host(adc[half:], F - half)
+    assert len(d0) > 0 and d0.tobytes() == d1.tobytes()
+    assert np.concatenate([a, b]).tobytes() == d0.tobytes()
