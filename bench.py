@@ -491,7 +491,7 @@ def run_stream(args, env):
                          "note": "SURVEY.md 8d: cfg5 is latency-bound; the figure to read is config.latency_us"},
             "e2e": {"value": sensors_total * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": F * ctx.frame_shorts * 2,
                     "d2h_bytes_per_step": F * 32 + 24 * n_det, "steps": K, "api": "mmw_process_host, 1 frame per call"},
-            "gpu_launches": K * F * ctx.info.kernels_per_batch, "clocks": clocks,
+            "gpu_launches": K * F * (ctx.info.kernels_per_batch + 1), "clocks": clocks,      # +1: power_sum_kernel of the antenna-split Doppler path
         }
         if not args.no_cpu_baseline and world == 1:
             orc = entry.load_oracle()

@@ -57,6 +57,8 @@ struct mmw_ctx {
     float2 *d_rs;
     float2 *d_cube;
     float *d_pmap;
+    float *d_psplit;         // per-antenna power maps of the antenna-split path for small batches (lazy)
+    int psplit_frames;       // frames d_psplit holds
     uint32_t *d_mask;
     float *d_noise;
     uint32_t *d_keys;
@@ -163,7 +165,7 @@ void mmw_destroy(mmw_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
-    cudaFree(c->d_adc); cudaFree(c->d_base); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_mask);
+    cudaFree(c->d_adc); cudaFree(c->d_base); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_psplit); cudaFree(c->d_mask);
     cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_scratch);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto &h : c->h_ring) if (h) cudaFreeHost(h);
@@ -367,7 +369,31 @@ static int run_front(mmw_ctx *c, const int16_t *adc_dev, int first, int n, cudaE
     if (stage_ev) CK(cudaEventRecord(stage_ev[0], st));
     CK(launch_range_fft(p, adc, rs, n, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[1], st));
-    CK(launch_doppler_fft(p, rs, cube, c->d_pmap + (size_t)first * M, n, st));
+    bool split = !cube && doppler_prefers_split(p, n);
+    if (split && n > c->psplit_frames) {
+        // per-antenna maps for the largest batch that still prefers the split, if that stays modest
+        int cap = n;
+        while (cap < c->cfg.max_frames && doppler_prefers_split(p, cap + 1)) ++cap;
+        const size_t bytes = (size_t)cap * p.A * M * sizeof(float);
+        if (bytes <= ((size_t)128 << 20)) {
+            if (c->d_psplit) { cudaFree(c->d_psplit); c->workspace_bytes -= (size_t)c->psplit_frames * p.A * M * sizeof(float); }
+            c->d_psplit = nullptr;
+            c->psplit_frames = 0;
+            int rc = dev_alloc(c, &c->d_psplit, (size_t)cap * p.A * M);
+            if (rc) return rc;
+            c->psplit_frames = cap;
+        } else {
+            split = false;
+        }
+    }
+    if (split) {
+        PlanDev q = p;                                   // [F][A][Sp][C] read as F*A single-antenna frames
+        q.A = 1;
+        CK(launch_doppler_fft(q, rs, nullptr, c->d_psplit, n * p.A, st));
+        CK(launch_power_sum(p, c->d_psplit, c->d_pmap + (size_t)first * M, n, st));
+    } else {
+        CK(launch_doppler_fft(p, rs, cube, c->d_pmap + (size_t)first * M, n, st));
+    }
     if (stage_ev) CK(cudaEventRecord(stage_ev[2], st));
     CK(launch_cfar(p, c->d_pmap + (size_t)first * M, c->d_mask + (size_t)first * (M / 32), c->d_noise + (size_t)first * M, n, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[3], st));

@@ -93,6 +93,9 @@ __device__ __forceinline__ void st_global_f2(float2 *p, float2 v)
 // ---------------------------------------------------------------------------
 cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st);
 cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st);
+// small batches: K2 over F*A single-antenna frames into per-antenna maps, then the ordered sum (mmw_pipeline.cu)
+bool doppler_prefers_split(const PlanDev &p, int n_frames);
+cudaError_t launch_power_sum(const PlanDev &p, const float *per_antenna, float *pmap, int n_frames, cudaStream_t st);
 // everything stages 3/4 read and write (device pointers)
 struct DetectBuffers {
     const float2 *rs;

@@ -236,6 +236,13 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
 // ---------------------------------------------------------------------------
 // K2: Doppler FFT + non-coherent integration
 // ---------------------------------------------------------------------------
+// |X|^2 and the running sum over antennas with the roundings pinned (no FMA contraction across the two), so that the
+// one-pass kernels and the antenna-split path for small batches (per-antenna maps + power_sum_kernel) give the same bits.
+__device__ __forceinline__ float accumulate_power(float acc, float2 v)
+{
+    return __fadd_rn(acc, __fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)));
+}
+
 // INPLACE: pass 1 writes its outputs back into the staging row it read (a thread reads and writes the same R1
 // addresses, so there is no hazard), which frees the separate work buffer: the same footprint then holds three
 // staging buffers instead of two, i.e. two loads in flight per CTA while a third is being transformed.
@@ -394,7 +401,7 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
 #pragma unroll
                     for (int k2 = 0; k2 < R2; ++k2) {
                         const float2 v = y[bitrev(k2, LR2)];
-                        acc[ui][k2] += v.x * v.x + v.y * v.y;
+                        acc[ui][k2] = accumulate_power(acc[ui][k2], v);
                     }
                     if (cube != nullptr) {
                         float2 *o = cube + (((size_t)f * A + a) * (size_t)N + k1) * Sp + r0 + row;
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p,
 #pragma unroll
                 for (int k2 = 0; k2 < R2; ++k2) {
                     const float2 v = y[bitrev(k2, LR2)];
-                    acc[u][k2] += v.x * v.x + v.y * v.y;
+                    acc[u][k2] = accumulate_power(acc[u][k2], v);
                 }
             }
             __syncwarp();
@@ -566,6 +573,26 @@ __global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p,
 #pragma unroll
             for (int k2 = 0; k2 < R2; ++k2) po[(size_t)(k1 + R1 * k2) * Sp] = acc[u][k2];
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// antenna-split path for small batches (latency mode)
+// ---------------------------------------------------------------------------
+// A tile of K2 walks its antennas one after the other, so a batch of one or a few frames occupies a handful of CTAs for
+// A steps each (one 256 x 128 x 12 frame: 16 CTAs x 12 steps).  For such batches the same kernels are launched over
+// F*A single-antenna "frames" — [F][A][Sp][C] is [F*A][1][Sp][C] — which spreads the steps over F*A times as many CTAs,
+// and the per-antenna power maps are then summed in ascending antenna order (the order and roundings of the one-pass
+// accumulation, see accumulate_power).
+__global__ void __launch_bounds__(256) power_sum_kernel(const float *__restrict__ per_antenna, float *__restrict__ pmap, int A, size_t M,
+                                                        size_t total)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / M, m = i - f * M;
+        const float *src = per_antenna + f * (size_t)A * M + m;
+        float acc = 0.f;
+        for (int a = 0; a < A; ++a) acc = __fadd_rn(acc, src[(size_t)a * M]);
+        pmap[i] = acc;
     }
 }
 
@@ -620,6 +647,20 @@ static int sm_count()
         if (count[dev] <= 0) count[dev] = 148;
     }
     return count[dev];
+}
+
+bool doppler_prefers_split(const PlanDev &p, int n_frames)
+{
+    // fewer tiles than half the SMs (tiles are 16 range bins or the equivalent number of warp-private tiles)
+    return p.A > 1 && (long long)n_frames * (p.Sp / 16) * 2 <= sm_count();
+}
+
+cudaError_t launch_power_sum(const PlanDev &p, const float *per_antenna, float *pmap, int n_frames, cudaStream_t st)
+{
+    const size_t M = (size_t)p.Sp * p.Cp, total = M * n_frames;
+    const int grid = (int)((total + 255) / 256 < (size_t)sm_count() * 8 ? (total + 255) / 256 : (size_t)sm_count() * 8);
+    power_sum_kernel<<<grid, 256, 0, st>>>(per_antenna, pmap, p.A, M, total);
+    return cudaGetLastError();
 }
 
 template <typename K>
