@@ -794,11 +794,16 @@ cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames
         if (e != cudaSuccess) return e;
         configured[wide] = bytes;
     }
+    // persistent grids sized for the resident CTAs; a one- or two-frame batch (latency mode) cannot feed that many and
+    // pays for every CTA it launches, so the grid also scales with the frame count
+    const int by_frames = n_frames * 64 < sm_count ? sm_count : n_frames * 64;
+    const int grid_wide = sm_count * 2 < by_frames ? sm_count * 2 : by_frames;
+    const int grid_narrow = sm_count * 4 < by_frames ? sm_count * 4 : by_frames;
     if (wide)
-        measure_wide_kernel<<<sm_count * 2, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask,
+        measure_wide_kernel<<<grid_wide, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask,
                                                                   b.keys, b.offsets, b.dense, b.ticket + 1, n_frames, dense_cap);
     else
-        measure_kernel<<<sm_count * 4, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask, b.keys,
+        measure_kernel<<<grid_narrow, kMeasNT, bytes, st>>>(p, b.rs, p.keep_cube ? b.cube : nullptr, b.pmap, b.noise_map, b.mask, b.keys,
                                                              b.offsets, b.dense, b.ticket + 1, n_frames, dense_cap);
     return cudaGetLastError();
 }
