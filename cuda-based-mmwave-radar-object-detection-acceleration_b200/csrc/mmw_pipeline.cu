@@ -44,14 +44,15 @@ void plan_radices(int n, int *r1, int *r2)
 // ---------------------------------------------------------------------------
 // K1: range FFT
 // ---------------------------------------------------------------------------
-template <int N, int BT, int NSTAGE>
+template <int N, int BT, int NSTAGE, bool BASE = false>
 struct RangeSmem {
     static constexpr int kStageStride = 4 * N + 16;                 // bytes per staged int16 row
     static constexpr int kOffTw = 16;
     static constexpr int kOffWin = kOffTw + 8 * N;
     static constexpr int kOffStage = kOffWin + 4 * N;
     static constexpr int kStageBytes = BT * kStageStride;
-    static constexpr int kOffWork = kOffStage + NSTAGE * kStageBytes;
+    static constexpr int kOffBase = kOffStage + NSTAGE * kStageBytes;   // BASE: the tile's rows of the base frame, staged alongside
+    static constexpr int kOffWork = kOffBase + (BASE ? NSTAGE * kStageBytes : 0);
     static constexpr int kBytes = kOffWork + BT * (N + 1) * 8;
 };
 
@@ -59,23 +60,26 @@ struct RangeSmem {
 // PAD : n_samples < N (zero padding needs a bound check per load); CT: compile-time n_chirps, 0 = run time.
 // NSTAGE = 1: one staging buffer, refilled behind pass 2; NSTAGE = 2: double buffer, refilled a whole tile ahead.
 // BASE: static-clutter removal — p.base_adc (one frame in capture format) is subtracted sample by sample, in integers,
-// before the window (the reference's base-frame subtraction, acceleration.cu:152-166, for every antenna).  The base frame
-// is a few MB read by every CTA, so it is served from L2 with plain read-only loads rather than staged.
+// before the window (the reference's base-frame subtraction, acceleration.cu:152-166, for every antenna).  The tile's
+// rows of the base frame are staged by the same TMA copies as the capture rows (they come from L2: the base frame is a
+// few MB read by every CTA); reading them with per-lane global loads instead costs 4x sector over-fetch and +70 % time.
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE>
-__global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
+__global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
                                                             int n_tiles)
 {
     static_assert(R1 * R2 == N, "plan");
-    using L = RangeSmem<N, BT, NSTAGE>;
+    using L = RangeSmem<N, BT, NSTAGE, BASE>;
     constexpr int NT = NW * 32;
     constexpr int SUBS = 32 / BT;
     constexpr int NSLOT = NW * SUBS;
     constexpr int LR1 = ilog2(R1), LR2 = ilog2(R2);
+
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     float2 *tw = reinterpret_cast<float2 *>(smem + L::kOffTw);
     float *win = reinterpret_cast<float *>(smem + L::kOffWin);
     unsigned char *stage = smem + L::kOffStage;
+    unsigned char *bstage = smem + L::kOffBase;                      // BASE only
     float2 *work = reinterpret_cast<float2 *>(smem + L::kOffWork);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -92,12 +96,16 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
         uint64_t *b = &bar[it % NSTAGE];
         if (lane == 0) {
             fence_proxy_async();
-            mbar_arrive_expect_tx(b, (uint32_t)(nrows * S * 4));
+            mbar_arrive_expect_tx(b, (uint32_t)(nrows * S * 4) * (BASE ? 2u : 1u));
         }
         __syncwarp();
         if (lane < nrows) {
             const int16_t *src = adc + (((size_t)f * C + c0 + lane) * A + a) * (size_t)(2 * S);
             bulk_g2s(stage + (it % NSTAGE) * L::kStageBytes + lane * L::kStageStride, src, (uint32_t)(S * 4), b);
+            if constexpr (BASE) {
+                const int16_t *bsrc = p.base_adc + ((size_t)(c0 + lane) * A + a) * (size_t)(2 * S);
+                bulk_g2s(bstage + (it % NSTAGE) * L::kStageBytes + lane * L::kStageStride, bsrc, (uint32_t)(S * 4), b);
+            }
         }
     };
 
@@ -125,9 +133,7 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
         if (NSTAGE == 2 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
         mbar_wait(&bar[it % NSTAGE], (uint32_t)((it / NSTAGE) & 1));
         const unsigned char *srow = stage + (it % NSTAGE) * L::kStageBytes + row * L::kStageStride;
-        const unsigned char *brow = nullptr;
-        if constexpr (BASE)
-            brow = reinterpret_cast<const unsigned char *>(p.base_adc) + ((size_t)min(c0 + row, C - 1) * A + (fa % A)) * (size_t)(4 * S);
+        const unsigned char *brow = BASE ? bstage + (it % NSTAGE) * L::kStageBytes + row * L::kStageStride : nullptr;
 
         // ---- pass 1: R2 butterflies of radix R1 over stride R2, reading the staged int16 rows ----
         if constexpr (PAIR) {
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
                         const float2 w = *reinterpret_cast<const float2 *>(win + n);
                         int i0 = (short)(raw.x & 0xffffu), q0 = (short)(raw.y & 0xffffu), i1 = (int)raw.x >> 16, q1 = (int)raw.y >> 16;
                         if constexpr (BASE) {
-                            const uint2 rb = __ldg(reinterpret_cast<const uint2 *>(brow + 4 * n));
+                            const uint2 rb = *reinterpret_cast<const uint2 *>(brow + 4 * n);
                             i0 -= (short)(rb.x & 0xffffu); q0 -= (short)(rb.y & 0xffffu);
                             i1 -= (int)rb.x >> 16;         q1 -= (int)rb.y >> 16;
                         }
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE>::kBytes
                         int iv = odd ? ((int)raw.x >> 16) : (int)(short)(raw.x & 0xffffu);
                         int qv = odd ? ((int)raw.y >> 16) : (int)(short)(raw.y & 0xffffu);
                         if constexpr (BASE) {
-                            const uint2 rb = __ldg(reinterpret_cast<const uint2 *>(brow + 4 * (n - odd)));
+                            const uint2 rb = *reinterpret_cast<const uint2 *>(brow + 4 * (n - odd));
                             iv -= odd ? ((int)rb.x >> 16) : (int)(short)(rb.x & 0xffffu);
                             qv -= odd ? ((int)rb.y >> 16) : (int)(short)(rb.y & 0xffffu);
                         }
@@ -675,7 +681,7 @@ template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, in
 static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
     auto k = range_fft_kernel<N, R1, R2, BT, NW, PAIR, PAD, CT, NSTAGE, BASE>;
-    constexpr int bytes = RangeSmem<N, BT, NSTAGE>::kBytes;
+    constexpr int bytes = RangeSmem<N, BT, NSTAGE, BASE>::kBytes;
     static int per_sm_dev[kMaxDevices] = {0};
     int &per_sm = per_sm_dev[current_device()];
     if (!per_sm) {
@@ -691,12 +697,13 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
 }
 
 // picks the PAD / compile-time-chirps specialisation
-template <int N, int R1, int R2, int BT, int NW, bool PAIR, int CT0, int CT1, int NSTAGE = 1>
+// BBT / BNW: tile rows and warps of the static-clutter-removal instantiation (the second staging buffer has to fit)
+template <int N, int R1, int R2, int BT, int NW, bool PAIR, int CT0, int CT1, int NSTAGE = 1, int BBT = BT, int BNW = NW>
 static cudaError_t run_range(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
     if (p.base_adc != nullptr) {          // static-clutter removal: one generic instantiation per padding mode
-        if (p.S == N) return run_range_t<N, R1, R2, BT, NW, PAIR, false, 0, NSTAGE, true>(p, adc, rs, n_frames, st);
-        return run_range_t<N, R1, R2, BT, NW, PAIR, true, 0, NSTAGE, true>(p, adc, rs, n_frames, st);
+        if (p.S == N) return run_range_t<N, R1, R2, BBT, BNW, PAIR, false, 0, NSTAGE, true>(p, adc, rs, n_frames, st);
+        return run_range_t<N, R1, R2, BBT, BNW, PAIR, true, 0, NSTAGE, true>(p, adc, rs, n_frames, st);
     }
     if (p.S == N) {
         if (CT0 && p.C == CT0) return run_range_t<N, R1, R2, BT, NW, PAIR, false, CT0, NSTAGE>(p, adc, rs, n_frames, st);
@@ -792,10 +799,10 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     // double-buffered staging (NSTAGE = 2) and BT = 8 tiles were measured slower for 256 and 512 points
     // (profiles/experiments/r1_k1_variants_sweep.log); the single-buffer BT = 16 shape stays
     case 256:  return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
-    case 512:  return run_range<512, 16, 32, 16, 8, true, 256, 0>(p, adc, rs, n_frames, st);
+    case 512:  return run_range<512, 16, 32, 16, 8, true, 256, 0, 1, 8, 4>(p, adc, rs, n_frames, st);
     // 1024 points: a 16-row tile needs 209 KB (one CTA per SM); 8 rows fit two CTAs per SM and measured 2.4 % faster
     // (profiles/experiments/r1_cfg4_tile_sweep.log)
-    case 1024: return run_range<1024, 32, 32, 8, 8, false, 512, 0>(p, adc, rs, n_frames, st);
+    case 1024: return run_range<1024, 32, 32, 8, 8, false, 512, 0, 1, 4, 4>(p, adc, rs, n_frames, st);
     default:   return cudaErrorInvalidValue;
     }
 }

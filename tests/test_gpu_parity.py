@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4          # relative to the maximum of the array being compared
 NEAR = 1e-5         # |P - thr| <= NEAR * thr  -> cell is "at threshold", excluded from the bit-exact claim
 
-# the last two exercise the 256-point angle FFT (A > 64: the cfg4 imaging array) and an odd antenna count
+# the next three exercise the 256-point angle FFT (A > 64: the cfg4 imaging array), an odd antenna count and the maximum A
 SHAPES = [(64, 64, 2), (100, 128, 4), (128, 64, 12), (256, 128, 4), (512, 256, 12), (1024, 64, 2), (64, 1024, 1), (256, 512, 3),
-          (64, 64, 192), (128, 128, 65),
+          (64, 64, 192), (128, 128, 65), (64, 64, 256),
           # ragged shapes: S a bare multiple of 4, C a bare multiple of 2, zero-padded to the next power of two on both axes
           (68, 66, 3), (500, 130, 2)]
 
