@@ -255,6 +255,27 @@ class Env:
             self.dist.destroy_process_group()
 
 
+def quick_chain(env, name, steps=10):
+    """device-resident frames/s of another chain workload, measured the same way (CUDA events, batch larger than L2); a
+    side note in the default line so that configs[1] is on record next to the headline configuration"""
+    torch, pkg, dev = env.torch, env.pkg, env.dev
+    w = WORKLOADS[name]
+    S, C, A, F = w["S"], w["C"], w["A"], w["F"]
+    ctx = pkg.RadarContext(S, C, A, F, max_det_per_frame=4096, device=env.local_rank)
+    adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=w["idx"] + 1)
+    torch.cuda.synchronize()
+    ctx.time_device(adc, F, 3)
+    total_ms, stage_ms = ctx.time_device(adc, F, steps, per_stage=True)
+    info = {"workload": f"{workload_text(name)} (BASELINE.json configs[{w['idx']}])", "frames_per_gpu_per_step": F, "steps": steps,
+            "value": F * steps / (total_ms * 1e-3), "unit": "frames/s", "ms_per_step": total_ms / steps,
+            "stage_ms": dict(zip(["range_fft_kernel", "doppler_fft_kernel", "cfar_kernel", "list_kernel+measure_kernel"], [x / steps for x in stage_ms])),
+            "pipeline_frac_of_measured_hbm_peak": int(ctx.info.algorithmic_bytes_per_frame) * F * steps / (total_ms * 1e-3) / 1e9 / peaks()[0]}
+    ctx.close()
+    del adc
+    torch.cuda.empty_cache()
+    return info
+
+
 def run_chain(args, env):
     """cfg2 / cfg3 / cfg4: batches through the whole chain"""
     torch, pkg, dev, rank, world = env.torch, env.pkg, env.dev, env.rank, env.world
@@ -380,6 +401,11 @@ def run_chain(args, env):
             "gpu_launches": K * (ctx.info.kernels_per_batch + (1 if world > 1 else 0)),
             "clocks": clocks,
         }
+        if args.workload == "cfg3" and world == 1 and not args.no_other:
+            ctx.close()
+            del adc
+            torch.cuda.empty_cache()
+            line["other_workloads"] = {"cfg2": quick_chain(env, "cfg2")}
         if not args.no_cpu_baseline and world == 1:
             orc = entry.load_oracle()
             orc.build()
@@ -590,6 +616,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames (cfg5: sensors) per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="cfg3: skip the side measurement of cfg2 (configs[1])")
     ap.add_argument("--no-graph", action="store_true", help="cfg5: launch the kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--keep-cube", action="store_true", help="materialise the Doppler cube in HBM (default: fused)")
     args = ap.parse_args()
