@@ -218,10 +218,34 @@ class Env:
         os.dup2(2, 1)
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.numa = self.bind_to_gpu_numa_node()
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", rank=self.rank, world_size=self.world, device_id=self.dev)
         self.pkg = entry.load_package()
+
+    def bind_to_gpu_numa_node(self):
+        """Multi-rank runs: pin this process (and, by first touch, its pinned host buffers) to the CPUs of the NUMA node
+        its GPU hangs off, so that the H2D copies of the end-to-end path do not cross sockets.  Returns the node or None."""
+        if self.world == 1:
+            return None
+        try:
+            pr = self.torch.cuda.get_device_properties(self.local_rank)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+            if node < 0:
+                return None
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if not cpus:
+                return None
+            os.sched_setaffinity(0, cpus)
+            return node
+        except (OSError, ValueError, AttributeError):
+            return None
 
     def sync_all(self):
         self.torch.cuda.synchronize()
@@ -380,7 +404,7 @@ def run_chain(args, env):
                 "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel on a side stream, overlapping the next step (overflow={gather_overflow})"),
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
                 "l2": f"inputs larger than L2: {F * 4 * N_adc / 1e6:.0f} MB int16 capture + {F * 8 * A * ctx.Sp * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
-                "ms_per_step_by_rank": [m / K for m in ms_by_rank],
+                "ms_per_step_by_rank": [m / K for m in ms_by_rank], "rank0_numa_node": env.numa,
                 "detections_per_step": n_det_step, "max_detections_in_one_frame": int(frame_counts.max()),
                 "max_det_per_frame": ctx.max_det_per_frame,
             },
