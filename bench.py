@@ -586,9 +586,10 @@ def run_legacy(args, env):
     want = np.array([orc.legacy_frame(distinct[1 + f], base)[1] for f in range(8)])
     assert np.array_equal(got[:8], want), "legacy raw bins differ from the reference CPU path"
     fps = world * F * K / (ms * 1e-3)
-    # e2e (a): batched host entry point, pinned-free (the library stages); (b) the reference's calling pattern: one cudaProcessing per frame
+    # e2e (a): batched host entry point from pinned host memory; (b) the reference's calling pattern: one cudaProcessing per frame
     n_host = min(F, 1024)
-    host = cap[:n_host]
+    host_pinned = torch.from_numpy(cap[:n_host]).pin_memory()       # the contract's e2e: inputs in pinned host memory
+    host = host_pinned.numpy()
     pkg.api.legacy_process_frames(host, base)
     t0 = time.perf_counter()
     e2e_steps = max(3, min(K, 10))
