@@ -473,6 +473,15 @@ int mmw_process_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
     if (rc) return rc;
     if (((uintptr_t)adc_dev & 15u) != 0) { set_last_error("mmw_process_device: adc_dev must be 16-byte aligned"); return MMW_ERR_ARG; }
     CK(cudaSetDevice(c->device));
+    {   // a host pointer here would fault inside the first kernel: refuse it up front
+        cudaPointerAttributes at;
+        const cudaError_t e = cudaPointerGetAttributes(&at, adc_dev);
+        if (e != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+            cudaGetLastError();
+            set_last_error("mmw_process_device: adc_dev is not a device pointer (use mmw_process_host for host captures)");
+            return MMW_ERR_ARG;
+        }
+    }
     return run_batch_graphed(c, adc_dev, n_frames);
 }
 

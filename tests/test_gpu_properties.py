@@ -166,3 +166,13 @@ def test_contexts_on_two_devices_in_one_process(pkg, batches):
             b, _ = c1.process_host(adc[half:], F - half)
     assert len(d0) > 0 and d0.tobytes() == d1.tobytes()
     assert np.concatenate([a, b]).tobytes() == d0.tobytes()
+
+
+def test_process_device_refuses_host_pointers(pkg, batches):
+    S, C, A, F = FULL[0]
+    adc = batches[(S, C, A)]
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        with pytest.raises(pkg.RadarError, match="not a device pointer"):
+            ctx.process_device(int(adc.ctypes.data) & ~15, F)
+        good, _ = ctx.process_host(adc, F)                       # the context is still usable afterwards
+        assert len(good) > 0
