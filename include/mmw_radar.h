@@ -17,11 +17,17 @@
  *                                 range / Doppler / CFAR / angle chain instead of one flat FFT.
  *   mmw_process_device            same, for captures already resident in HBM.
  *   mmw_read_* / mmw_copy_*       the reference's D2H of the spectrum (acceleration.cu:519).
+ *   mmw_set_base_frame            cudaDataExtension_kernel's base-frame subtraction (acceleration.cu:152-166), all antennas.
+ *   mmw_process_capture_file      the fopen / fread / one-call-per-frame loop of cudaTiming() (cudaBenchMarking.cpp:339-378).
+ *   mmw_to_physical               the distance formula (cudaBenchMarking.cpp:301-303) and the constants of :10-19.
  *   mmw_legacy_*                  see mmw_legacy.h.
  *
  * Frame format (identical to the reference capture files, cudaBenchMarking.cpp:156-180):
  * little-endian int16, per frame [chirp][antenna][sample], samples in groups of four shorts
  * [I(2m) I(2m+1) Q(2m) Q(2m+1)]; frames concatenated without header.
+ *
+ * Threading: a context is not thread-safe — drive it from one host thread at a time; different contexts (also on
+ * different GPUs, mmw_config.device) are independent and may be used concurrently.  mmw_last_error() is per thread.
  *
  * All functions return MMW_OK (0) or a negative error code; mmw_last_error() gives the text
  * of the calling thread's last failure.  There is no CPU fallback: without a CUDA device every
