@@ -507,6 +507,35 @@ def run_stream(args, env):
         n_det = tick_host(lat)
     t_e2e = env.max_over_ranks(time.perf_counter() - t0)
     lat_us = np.sort(np.array(lat)) * 1e6
+    # the same calls split in two (mmw_submit_host / mmw_wait) over a ring of contexts: `depth` frames in flight, the upload
+    # of frame k+1 under the kernels and read-back of frame k
+    depth = 2
+    ring = [pkg.RadarContext(S, C, A, 1, max_det_per_frame=4096, device=env.local_rank) for _ in range(depth)]
+    for c in ring:
+        c.set_graph_mode(not args.no_graph)
+
+    def tick_pipelined():
+        n = 0
+        for i in range(F + depth):
+            c = ring[i % depth]
+            if i >= depth:
+                n += len(c.wait(out=out)[0])
+            if i < F:
+                c.set_frame_offset(sensors[i])
+                c.submit_host(frames[i], 1)
+        return n
+
+    for _ in range(W):
+        tick_pipelined()
+    env.sync_all()
+    t0 = time.perf_counter()
+    n_det_pipe = 0
+    for _ in range(K):
+        n_det_pipe = tick_pipelined()
+    t_pipe = env.max_over_ranks(time.perf_counter() - t0)
+    for c in ring:
+        c.close()
+    assert n_det_pipe == n_det, (n_det_pipe, n_det)
     # the same tick as one batch (all sensors' frames together)
     big = np.empty(F * ctx.max_det_per_frame, pkg.DET_DTYPE)
     ctx.set_frame_offset(0)
@@ -531,7 +560,8 @@ def run_stream(args, env):
                 "latency_us": {"p50": float(lat_us[len(lat_us) // 2]), "p99": float(lat_us[min(len(lat_us) - 1, int(0.99 * len(lat_us)))]),
                                "max": float(lat_us[-1]), "samples": int(len(lat_us)),
                                "what": "wall clock of one mmw_process_host(1 frame) call: pinned host -> H2D -> 5 kernels -> D2H -> return"},
-                "tick_as_one_batch_ms": tick_batched_ms, "realtime_margin_x": (1000.0 / 30.0) / (t_e2e / K * 1e3),
+                "tick_as_one_batch_ms": tick_batched_ms, "realtime_margin_x": (1000.0 / 30.0) / (t_pipe / K * 1e3),
+                "one_call_per_frame_synchronous_frames_per_s": sensors_total * K / t_e2e,
                 "l2": "latency mode: one 1.5 MB frame per call (fits L2 by construction; this workload is launch/PCIe-latency bound, not HBM bound)",
                 "detections_last_tick": n_det,
             },
@@ -539,8 +569,9 @@ def run_stream(args, env):
                          "peak": peak, "unit": "GB/s", "frac": b_alg * sensors_total * K / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
                          "note": "SURVEY.md 8d: cfg5 is latency-bound; the figure to read is config.latency_us"},
-            "e2e": {"value": sensors_total * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": F * ctx.frame_shorts * 2,
-                    "d2h_bytes_per_step": F * 32 + 24 * n_det, "steps": K, "api": "mmw_process_host, 1 frame per call"},
+            "e2e": {"value": sensors_total * K / t_pipe, "unit": "frames/s", "h2d_bytes_per_step": F * ctx.frame_shorts * 2,
+                    "d2h_bytes_per_step": F * 32 + 24 * n_det, "steps": K,
+                    "api": f"mmw_submit_host + mmw_wait, 1 frame per call, {depth} frames in flight (one context each)"},
             "gpu_launches": K * F * (ctx.info.kernels_per_batch + 1), "clocks": clocks,      # +1: power_sum_kernel of the antenna-split Doppler path
         }
         if not args.no_cpu_baseline and world == 1:

@@ -36,7 +36,7 @@ assert DET_DTYPE.itemsize == 24
 C_ABI_SYMBOLS = [
     "mmw_default_config", "mmw_create", "mmw_destroy", "mmw_last_error", "mmw_get_info",
     "mmw_set_windows", "mmw_get_windows", "mmw_set_frame_offset", "mmw_stream", "mmw_use_stream",
-    "mmw_process_device", "mmw_process_host", "mmw_read_detections", "mmw_read_counts",
+    "mmw_process_device", "mmw_process_host", "mmw_submit_host", "mmw_wait", "mmw_read_detections", "mmw_read_counts",
     "mmw_device_results", "mmw_device_result_block", "mmw_merge_gathered", "mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map",
     "mmw_copy_cfar_mask", "mmw_time_device",
     "mmw_set_graph_mode", "mmw_set_base_frame", "mmw_process_capture_file", "mmw_default_radar_params", "mmw_to_physical",
@@ -114,6 +114,8 @@ def load(build_if_missing: bool = True):
     L.mmw_use_stream.argtypes = [vp, vp]
     L.mmw_process_device.argtypes = [vp, vp, C.c_int]
     L.mmw_process_host.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip]
+    L.mmw_submit_host.argtypes = [vp, vp, C.c_int]
+    L.mmw_wait.argtypes = [vp, vp, C.c_int, ip]
     L.mmw_read_detections.argtypes = [vp, vp, C.c_int, ip]
     L.mmw_read_counts.argtypes = [vp, vp, C.c_int]
     L.mmw_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -289,6 +291,27 @@ class RadarContext:
 
     def to_physical(self, dets: np.ndarray, params: RadarParams | None = None) -> np.ndarray:
         return to_physical(dets, self.Sp, self.Cp, params)
+
+    def submit_host(self, adc_host, n_frames: int):
+        """First half of process_host: queue upload + chain + read-back, return at once (keep adc_host alive and pinned)."""
+        if isinstance(adc_host, np.ndarray):
+            ptr, n = adc_host.ctypes.data, adc_host.size
+            if adc_host.dtype != np.int16 or not adc_host.flags["C_CONTIGUOUS"]:
+                raise ValueError("submit_host needs a C-contiguous int16 array (it is read after the call returns)")
+        else:
+            ptr, n = adc_host.data_ptr(), adc_host.numel()
+        if n < n_frames * self.frame_shorts:
+            raise ValueError("capture buffer shorter than n_frames frames")
+        _check(self._L.mmw_submit_host(self._h, C.c_void_p(ptr), n_frames))
+
+    def wait(self, det_capacity: int | None = None, out: np.ndarray | None = None):
+        """Second half of process_host: block until the submitted batch is done. Returns (detections, overflow_flag)."""
+        cap = det_capacity if det_capacity is not None else self.max_frames * self.max_det_per_frame
+        dets = out if out is not None else np.empty(cap, DET_DTYPE)
+        cap = min(cap, dets.size)
+        n_det = C.c_int(0)
+        rc = _check(self._L.mmw_wait(self._h, _np_ptr(dets), cap, C.byref(n_det)), True)
+        return dets[: n_det.value], rc == MMW_ERR_OVERFLOW
 
     def read_detections(self, det_capacity: int | None = None):
         cap = det_capacity if det_capacity is not None else self.max_frames * self.max_det_per_frame

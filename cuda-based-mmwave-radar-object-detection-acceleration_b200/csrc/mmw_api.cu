@@ -75,6 +75,8 @@ struct mmw_ctx {
     uint32_t *h_header;
     mmw_detection *h_dense;
     uint32_t guess_det;       // records fetched speculatively with the header (adapts to the last batch)
+    uint32_t fetched;         // records covered by the D2H queued by enqueue_fetch
+    int submitted;            // a batch queued by mmw_submit_host is waiting for mmw_wait
     cudaStream_t copy_stream; // H2D of host captures, overlapped chunk-wise with the kernels
     cudaEvent_t chunk_ev[kMaxChunks];
     int dense_cap;
@@ -395,7 +397,7 @@ static int run_front(mmw_ctx *c, const int16_t *adc_dev, int first, int n, cudaE
         CK(launch_doppler_fft(p, rs, cube, c->d_pmap + (size_t)first * M, n, st));
     }
     if (stage_ev) CK(cudaEventRecord(stage_ev[2], st));
-    CK(launch_cfar(p, c->d_pmap + (size_t)first * M, c->d_mask + (size_t)first * (M / 32), c->d_noise + (size_t)first * M, n, st));
+    CK(launch_cfar(p, c->d_pmap + (size_t)first * M, c->d_mask + (size_t)first * (M / 32), c->d_noise + (size_t)first * M, n, c->sm_count, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[3], st));
     return MMW_OK;
 }
@@ -486,12 +488,20 @@ int mmw_process_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
 }
 
 // One D2H brings the header and the first `guess_det` records; a second copy is needed only when
-// the batch produced more than that (the guess follows the previous batch).
-static int fetch_results(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)
+// the batch produced more than that (the guess follows the previous batch).  Split in two so that a caller can
+// queue a batch (enqueue_fetch) and collect it later (finish_fetch).
+static int enqueue_fetch(mmw_ctx *c)
+{
+    const uint32_t guess = c->guess_det < (uint32_t)c->dense_cap ? c->guess_det : (uint32_t)c->dense_cap;
+    c->fetched = guess;
+    CK(cudaMemcpyAsync(c->h_result, c->d_result, kResultHeaderBytes + (size_t)guess * sizeof(mmw_detection), cudaMemcpyDeviceToHost, c->stream));
+    return MMW_OK;
+}
+
+static int finish_fetch(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)
 {
     cudaStream_t st = c->stream;
-    uint32_t guess = c->guess_det < (uint32_t)c->dense_cap ? c->guess_det : (uint32_t)c->dense_cap;
-    CK(cudaMemcpyAsync(c->h_result, c->d_result, kResultHeaderBytes + (size_t)guess * sizeof(mmw_detection), cudaMemcpyDeviceToHost, st));
+    const uint32_t guess = c->fetched;
     CK(cudaStreamSynchronize(st));
     const uint32_t n_written = c->h_header[0];
     uint32_t n = n_written;
@@ -510,6 +520,13 @@ static int fetch_results(mmw_ctx *c, mmw_detection *dets, int det_capacity, int 
     if (rc == MMW_ERR_OVERFLOW)
         set_last_error("detection list truncated: %u of %u detections kept", n, c->h_header[1]);
     return rc;
+}
+
+static int fetch_results(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    int rc = enqueue_fetch(c);
+    if (rc) return rc;
+    return finish_fetch(c, dets, det_capacity, n_det);
 }
 
 // Host capture -> device results, asynchronous.  The capture goes up in chunks on a copy stream; stages 1-3 of chunk k
@@ -546,12 +563,32 @@ static int run_host_batch(mmw_ctx *c, const int16_t *adc_host, int n_frames)
 
 int mmw_process_host(mmw_ctx *c, const int16_t *adc_host, int n_frames, mmw_detection *dets, int det_capacity, int *n_det)
 {
-    int rc = check_batch_args(c, adc_host, n_frames, "mmw_process_host");
+    int rc = mmw_submit_host(c, adc_host, n_frames);
     if (rc) return rc;
+    return mmw_wait(c, dets, det_capacity, n_det);
+}
+
+int mmw_submit_host(mmw_ctx *c, const int16_t *adc_host, int n_frames)
+{
+    int rc = check_batch_args(c, adc_host, n_frames, "mmw_submit_host");
+    if (rc) return rc;
+    if (c->submitted) { set_last_error("mmw_submit_host: the previous batch has not been collected with mmw_wait"); return MMW_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     rc = run_host_batch(c, adc_host, n_frames);
     if (rc) return rc;
-    return fetch_results(c, dets, det_capacity, n_det);
+    rc = enqueue_fetch(c);
+    if (rc) return rc;
+    c->submitted = 1;
+    return MMW_OK;
+}
+
+int mmw_wait(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    if (!c) { set_last_error("mmw_wait: null context"); return MMW_ERR_ARG; }
+    if (!c->submitted) { set_last_error("mmw_wait: nothing submitted"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    c->submitted = 0;
+    return finish_fetch(c, dets, det_capacity, n_det);
 }
 
 // ---------------------------------------------------------------------------

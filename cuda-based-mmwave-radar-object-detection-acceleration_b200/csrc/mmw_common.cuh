@@ -110,7 +110,7 @@ struct DetectBuffers {
     unsigned int *ticket;   // [0] last-CTA-done counter of list_kernel, [1] work cursor of measure_kernel (both self-resetting)
     mmw_detection *dense;   // ordered detection list of the batch
 };
-cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, cudaStream_t st);
+cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, int sm_count, cudaStream_t st);
 cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st);
 cudaError_t launch_merge(const unsigned char *gathered, int n_ranks, size_t stride_bytes, unsigned char *merged, int merged_cap,
                          cudaStream_t st);

@@ -19,6 +19,8 @@
 // sum below therefore only ever ADDS training cells: per row a `full` window sum and a `ring` sum
 // (full minus the guard span, computed as left + right), then a column sum that takes `ring` rows
 // inside the Doppler guard and `full` rows outside it.
+#include <stdlib.h>
+
 #include "mmw_common.cuh"
 
 namespace mmw {
@@ -186,6 +188,229 @@ __global__ void __launch_bounds__(kCfarNT) cfar_kernel(PlanDev p, const float *_
     }
     __syncthreads();
     if (tid < kCfarRT && r0 + tid < Sp) mask[((size_t)f * (Cp / 32) + dblk) * Sp + r0 + tid] = words[tid];
+}
+
+// ---------------------------------------------------------------------------
+// K3, default geometry (guard 2x2, train 8x4), Sp % 64 == 0, Cp % 32 == 0: "walk" form.
+//
+// cfar_kernel above is instruction-bound (ncu: ~74 thread instructions per cell): independent 64 x 32 tiles re-stage
+// 1.9x their cells as halo, and the column pass reads 22 scalar shared-memory words per 4 cells.  Here the window is
+// split the other way round.  With F13 / R8 = the 13-row Doppler sum of one range column and its 8-row ring (13 minus
+// the 5 guard rows),
+//     noise_sum(r, d) = sum_{3 <= |dr| <= 10} F13[r + dr][d]  +  sum_{|dr| <= 2} R8[r + dr][d]
+// (the same training cells, still only ever added).  A CTA owns a strip of RT range bins x (16 * nchunk) Doppler bins of
+// one frame.  Everything is computed on float2 pairs = (strip column c, strip column c + RT/2) with packed fp32x2 adds,
+// so the two halves of the strip ride in the two halves of every instruction and no value is ever moved between them.
+//   phase A  one thread = one pair-column (lanes along range: plain coalesced global loads, no staging), walking down
+//            the Doppler axis 16 rows at a time with the last 12 input rows carried in registers; sliding 4- and
+//            5-sums by doubling: 100 FADD2 per 32 cells.
+//   phase B  one thread = SW pair-cells of one row: F13 / R8 / the cells come back as LDS.128 (two pair-columns each),
+//            sliding 8- and 5-sums by doubling, threshold test by sign (109 FADD2 per 16 cells at SW = 8).
+// Doppler wraps, range zero-fills (adding +0 is exact) and the training count is recounted near the range edges
+// exactly as above.  Every cell's sum is one fixed expression of the power map, independent of RT, nchunk and the
+// batch size.
+// ---------------------------------------------------------------------------
+template <int RT>
+struct WalkShape {
+    static constexpr int H = RT / 2;             // pair-cells per row
+    static constexpr int NP = H + 24;            // pair-columns incl. the 12-bin halo on either side (10 needed; 12 keeps 16-byte alignment)
+    static constexpr int CS = H + 34;            // row stride in float2; CS % 16 == 2 makes phase B's LDS.128 conflict-free
+    static constexpr int SW = 8;                 // pair-cells per phase-B task
+    static constexpr int NTASK = 16 * (H / SW);
+    static constexpr int NT = NTASK > ((NP + 31) & ~31) ? NTASK : ((NP + 31) & ~31);
+    static constexpr int SMEM = 3 * 16 * CS * 8 + H * 8 + RT * 4;
+    static_assert(CS % 16 == 2 && CS >= NP + 2, "row stride");
+};
+
+template <int RT, int MINB, int SPT>
+__global__ void __launch_bounds__(WalkShape<RT>::NT, MINB) cfar_walk_kernel(PlanDev p, const float *__restrict__ pmap, uint32_t *__restrict__ mask,
+                                                                            float *__restrict__ noise_map, int nchunk)
+{
+    using Sh = WalkShape<RT>;
+    constexpr int H = Sh::H, NP = Sh::NP, CS = Sh::CS, SW = Sh::SW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2 *sF = reinterpret_cast<float2 *>(smem);      // [16][CS]  F13 of (column c, column c + H)
+    float2 *sR = sF + 16 * CS;                          // ring sums, same layout
+    float2 *sC = sR + 16 * CS;                          // the cells themselves; phase B leaves each cell's noise estimate in its place
+    float2 *sInv = sC + 16 * CS;                        // [H]  1 / training-cell count of range bins (r0 + q, r0 + H + q)
+    uint32_t *words = reinterpret_cast<uint32_t *>(sInv + H);   // [RT]
+
+    const int tid = threadIdx.x;
+    const uint32_t Sp = SPT ? SPT : p.Sp, Cp = p.Cp;    // SPT: the row offsets of phase A's loads become immediates
+    const int r0 = blockIdx.x * RT;
+    const uint32_t dseg0 = blockIdx.y * 16 * nchunk;
+    const uint32_t f = blockIdx.z;
+    const float *pf = pmap + (size_t)f * Cp * Sp;
+
+    // phase A identity: pair-column tid = range bins (rX, rX + H)
+    const int rX = r0 - 12 + tid;
+    const bool colA = tid < NP;
+    const bool liveX = colA && rX >= 0 && rX < (int)Sp;
+    const bool liveY = colA && rX + H >= 0 && rX + H < (int)Sp;
+    const float *cx = pf + (liveX ? rX : 0), *cy = pf + (liveY ? rX + H : 0);
+    // phase B identity: row j of the chunk, pair-cells x0 .. x0 + SW - 1
+    const int j = tid & 15, x0 = (tid >> 4) * SW;
+    const bool taskB = tid < Sh::NTASK;
+
+    if (tid < H) {
+        float inv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = r0 + tid + u * H;
+            const int n_full = min(r + 10, (int)Sp - 1) - max(r - 10, 0) + 1;
+            const int n_guard = min(r + 2, (int)Sp - 1) - max(r - 2, 0) + 1;
+            inv[u] = 1.0f / (float)(13 * n_full - 5 * n_guard);            // 1/248 away from the range edges
+        }
+        sInv[tid] = make_float2(inv[0], inv[1]);
+    }
+    if (tid < RT) words[tid] = 0u;
+
+    float2 P[28];                            // P[i] = row dseg0 + 16 k - 6 + i of this pair-column
+#pragma unroll
+    for (int i = 0; i < 28; ++i) P[i] = make_float2(0.f, 0.f);
+    if (colA) {                              // run-in: the 12 rows before the segment's first new row
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const uint32_t o = ((dseg0 + Cp - 6 + i) & (Cp - 1)) * Sp;
+            if (liveX) P[16 + i].x = __ldg(cx + o);
+            if (liveY) P[16 + i].y = __ldg(cy + o);
+        }
+    }
+
+    for (int k = 0; k < nchunk; ++k) {
+        const uint32_t dk = dseg0 + 16 * k;
+        if (colA) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) P[i] = P[i + 16];
+            if (liveX && liveY && dk + 22 <= Cp) {       // the usual case: both columns inside the map, rows dk + 6 .. dk + 21 do not wrap
+                const float *px = cx + (dk + 6) * Sp, *py = cy + (dk + 6) * Sp;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) P[12 + i] = make_float2(__ldg(px + i * Sp), __ldg(py + i * Sp));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t o = ((dk + 6 + i) & (Cp - 1)) * Sp;
+                    P[12 + i] = make_float2(liveX ? __ldg(cx + o) : 0.f, liveY ? __ldg(cy + o) : 0.f);
+                }
+            }
+            float2 s2[27], s4[25];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) s2[i] = __fadd2_rn(P[i], P[i + 1]);
+#pragma unroll
+            for (int i = 0; i < 25; ++i) s4[i] = __fadd2_rn(s2[i], s2[i + 2]);      // rows i .. i+3
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {                                           // output row q; its centre is input row q + 6
+                const float2 ring = __fadd2_rn(s4[q], s4[q + 9]);                    // Doppler offsets -6..-3 and +3..+6
+                const float2 mid = __fadd2_rn(s4[q + 4], P[q + 8]);                  // offsets -2..+2
+                sR[q * CS + tid] = ring;
+                sF[q * CS + tid] = __fadd2_rn(ring, mid);
+                sC[q * CS + tid] = P[q + 6];
+            }
+        }
+        __syncthreads();
+        if (taskB) {
+            const float4 *f4 = reinterpret_cast<const float4 *>(sF + j * CS + x0);
+            const float4 *r4 = reinterpret_cast<const float4 *>(sR + j * CS + x0 + 8);
+            float4 *c4 = reinterpret_cast<float4 *>(sC + j * CS + x0 + 12);
+            const float4 *i4 = reinterpret_cast<const float4 *>(sInv + x0);
+            constexpr int NV = SW + 24;      // V[i] = F13 at pair-column x0 + i; pair-cell q sits at pair-column x0 + 12 + q
+            float2 V[NV], LR[SW];
+#pragma unroll
+            for (int i = 1; i < NV / 2 - 1; ++i) {
+                const float4 t = f4[i];
+                V[2 * i] = make_float2(t.x, t.y); V[2 * i + 1] = make_float2(t.z, t.w);
+            }
+            {
+                float2 a2[NV - 3], a4[NV - 5];
+#pragma unroll
+                for (int i = 2; i < NV - 3; ++i) a2[i] = __fadd2_rn(V[i], V[i + 1]);
+#pragma unroll
+                for (int i = 2; i < NV - 5; ++i) a4[i] = __fadd2_rn(a2[i], a2[i + 2]);   // columns i .. i+3
+#pragma unroll
+                for (int q = 0; q < SW; ++q)                                         // range offsets -10..-3 and +3..+10
+                    LR[q] = __fadd2_rn(__fadd2_rn(a4[q + 2], a4[q + 6]), __fadd2_rn(a4[q + 15], a4[q + 19]));
+            }
+            float2 W[SW + 8];                // W[i] = ring sum at pair-column x0 + 8 + i; pair-cell q uses W[q+2 .. q+6]
+#pragma unroll
+            for (int i = 1; i < SW / 2 + 4; ++i) {
+                const float4 t = r4[i];
+                W[2 * i] = make_float2(t.x, t.y); W[2 * i + 1] = make_float2(t.z, t.w);
+            }
+            float2 b2[SW + 5], b4[SW + 2];
+#pragma unroll
+            for (int i = 2; i < SW + 5; ++i) b2[i] = __fadd2_rn(W[i], W[i + 1]);
+#pragma unroll
+            for (int i = 2; i < SW + 2; ++i) b4[i] = __fadd2_rn(b2[i], b2[i + 2]);
+            const float2 alpha2 = make_float2(p.alpha, p.alpha);
+            // hit <=> cut > alpha * noise <=> alpha * noise - cut < 0 (the rounded difference of two floats has the sign of the
+            // exact one); the sign bits are shifted into hx / hy: after the loop bit (SW - 1 - q) = pair-cell q, x / y half
+            uint32_t hx = 0, hy = 0;
+#pragma unroll
+            for (int q2 = 0; q2 < SW / 2; ++q2) {
+                const float4 inv = i4[q2];
+                const float4 cc = c4[q2];
+                float2 nz[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int q = 2 * q2 + u;
+                    const float2 mid = __fadd2_rn(b4[q + 2], W[q + 6]);              // -2..+2 of the ring sums
+                    const float2 T = __fadd2_rn(LR[q], mid);
+                    nz[u] = __fmul2_rn(T, u ? make_float2(inv.z, inv.w) : make_float2(inv.x, inv.y));
+                    const float2 thr = __fmul2_rn(nz[u], alpha2);
+                    const float2 dlt = __ffma2_rn(u ? make_float2(cc.z, cc.w) : make_float2(cc.x, cc.y), make_float2(-1.f, -1.f), thr);
+                    hx = __funnelshift_l(__float_as_uint(dlt.x), hx, 1);
+                    hy = __funnelshift_l(__float_as_uint(dlt.y), hy, 1);
+                }
+                c4[q2] = make_float4(nz[0].x, nz[0].y, nz[1].x, nz[1].y);           // these cells belong to this task alone
+            }
+            // rare: record the hits
+            uint32_t h = hx | (hy << 16);
+            while (h) {
+                const int b = __ffs(h) - 1;
+                h &= h - 1;
+                const int q = SW - 1 - (b & 15), hi = b >> 4;
+                const float noise = reinterpret_cast<const float *>(c4)[2 * q + hi];
+                const int x = x0 + q + hi * H;                                       // range bin within the strip
+                const uint32_t d = dk + j;
+                atomicOr(&words[x], 1u << (d & 31));
+                noise_map[((size_t)f * Cp + d) * Sp + r0 + x] = noise;              // sparse: hit cells only
+            }
+        }
+        __syncthreads();
+        if ((k & 1) && tid < RT) {           // 32 Doppler rows done: one mask word per range bin
+            mask[((size_t)f * (Cp / 32) + ((dk - 16) >> 5)) * Sp + r0 + tid] = words[tid];
+            words[tid] = 0u;
+        }
+    }
+}
+
+template <int RT, int MINB, int SPT>
+static cudaError_t run_cfar_walk_t(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int nchunk, int n_frames, cudaStream_t st)
+{
+    using Sh = WalkShape<RT>;
+    if (Sh::SMEM > 48 * 1024) {
+        static bool configured_dev[kMaxDevices] = {false};
+        bool &configured = configured_dev[current_device()];
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(cfar_walk_kernel<RT, MINB, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sh::SMEM);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+    }
+    dim3 grid(p.Sp / RT, p.Cp / (16 * nchunk), n_frames);
+    cfar_walk_kernel<RT, MINB, SPT><<<grid, Sh::NT, Sh::SMEM, st>>>(p, pmap, mask, noise_map, nchunk);
+    return cudaGetLastError();
+}
+
+template <int RT, int MINB>
+static cudaError_t run_cfar_walk(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int nchunk, int n_frames, cudaStream_t st)
+{
+    switch (p.Sp) {
+    case 256:  return run_cfar_walk_t<RT, MINB, 256>(p, pmap, mask, noise_map, nchunk, n_frames, st);
+    case 512:  return run_cfar_walk_t<RT, MINB, 512>(p, pmap, mask, noise_map, nchunk, n_frames, st);
+    case 1024: return run_cfar_walk_t<RT, MINB, 1024>(p, pmap, mask, noise_map, nchunk, n_frames, st);
+    default:   return run_cfar_walk_t<RT, MINB, 0>(p, pmap, mask, noise_map, nchunk, n_frames, st);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -749,10 +974,39 @@ static int cfar_smem_bytes(const PlanDev &p)
     return (th_ * tw_ + 2 * th_ * kCfarRS) * 4 + kCfarRT * 4;
 }
 
-cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, cudaStream_t st)
+// MMW_K3_VARIANT (profiles/sweep_variants.py): 0 = pick by shape, 1 = always the tiled kernel, 2/3 = walk kernel forced to
+// 64- / 128-bin strips, +10 * nchunk to force the Doppler segment length
+static int cfar_variant()
 {
-    const int bytes = cfar_smem_bytes(p);
+    const char *e = getenv("MMW_K3_VARIANT");
+    return e ? atoi(e) : 0;
+}
+
+cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, int sm_count, cudaStream_t st)
+{
     const bool fixed = p.guard_r == 2 && p.guard_d == 2 && p.win_r_half == 10 && p.win_d_half == 6;
+    const int var = cfar_variant();
+    if (fixed && p.Sp % 64 == 0 && p.Cp % 32 == 0 && var != 1) {
+        // walk form.  Longer Doppler segments amortise the 12-row run-in (28 input rows for the first 16 outputs, 16
+        // after that), wider strips the 24-column halo; both are traded against having enough CTAs for every SM.
+        const long long cells = (long long)n_frames * p.Sp * p.Cp;
+        const long long want = (long long)sm_count * 8;
+        int rt = 64;
+        if (p.Sp % 128 == 0 && cells / (128 * 32) >= want) rt = 128;
+        if (p.Sp % 256 == 0 && cells / (256 * 32) >= want) rt = 256;
+        int nchunk = 2;
+        while (nchunk < 8 && p.Cp % (32 * nchunk) == 0 && cells / ((long long)rt * 32 * nchunk) >= want) nchunk *= 2;
+        if (var % 10 == 2) rt = 64;
+        if (var % 10 == 3 && p.Sp % 128 == 0) rt = 128;
+        if (var % 10 == 4 && p.Sp % 256 == 0) rt = 256;
+        if (var >= 10 && var / 10 % 2 == 0 && p.Cp % (16 * (var / 10)) == 0) nchunk = var / 10;
+        switch (rt) {
+        case 256: return run_cfar_walk<256, 3>(p, pmap, mask, noise_map, nchunk, n_frames, st);
+        case 128: return run_cfar_walk<128, 5>(p, pmap, mask, noise_map, nchunk, n_frames, st);
+        default:  return run_cfar_walk<64, 8>(p, pmap, mask, noise_map, nchunk, n_frames, st);
+        }
+    }
+    const int bytes = cfar_smem_bytes(p);
     static int configured_dev[kMaxDevices][2] = {{0}};
     int *configured = configured_dev[current_device()];
     if (bytes > configured[fixed]) {

@@ -129,6 +129,14 @@ int mmw_process_device(mmw_ctx *ctx, const int16_t *adc_dev, int n_frames);
 int mmw_process_host(mmw_ctx *ctx, const int16_t *adc_host, int n_frames,
                      mmw_detection *dets, int det_capacity, int *n_det);
 
+/* The two halves of mmw_process_host, for streaming with several batches in flight (one context per batch in flight,
+ * each with its own stream): mmw_submit_host queues the upload, the chain and the read-back of the result block and
+ * returns without waiting; mmw_wait blocks until that batch is done and hands out its detections.  The capture buffer
+ * must stay valid until mmw_wait returns and should be pinned (a pageable buffer makes the upload synchronous).
+ * One batch per context at a time: a second submit before the wait returns MMW_ERR_STATE. */
+int mmw_submit_host(mmw_ctx *ctx, const int16_t *adc_host, int n_frames);
+int mmw_wait(mmw_ctx *ctx, mmw_detection *dets, int det_capacity, int *n_det);
+
 /* After mmw_process_device: synchronises, then copies the ordered detection list. */
 int mmw_read_detections(mmw_ctx *ctx, mmw_detection *dets, int det_capacity, int *n_det);
 /* per-frame TRUE detection counts of the last batch (may exceed max_det_per_frame) */

@@ -176,3 +176,46 @@ def test_process_device_refuses_host_pointers(pkg, batches):
             ctx.process_device(int(adc.ctypes.data) & ~15, F)
         good, _ = ctx.process_host(adc, F)                       # the context is still usable afterwards
         assert len(good) > 0
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_submit_wait_two_batches_in_flight(pkg, batches, graph):
+    """mmw_submit_host / mmw_wait: frames streamed through two contexts (two in flight) give, frame by frame, the bytes
+    the synchronous mmw_process_host gives; a second submit or a wait with nothing queued is MMW_ERR_STATE."""
+    import torch
+
+    S, C, A, F = FULL[2]
+    adc = batches[(S, C, A)]
+    pinned = torch.empty(adc.shape, dtype=torch.int16, pin_memory=True)
+    pinned.copy_(torch.from_numpy(adc))
+    with pkg.RadarContext(S, C, A, 1) as sync_ctx:
+        sync_ctx.set_graph_mode(graph)
+        want = []
+        for f in range(F):
+            sync_ctx.set_frame_offset(f)
+            want.append(sync_ctx.process_host(pinned[f], 1)[0].copy())
+    ring = [pkg.RadarContext(S, C, A, 1) for _ in range(2)]
+    try:
+        for c in ring:
+            c.set_graph_mode(graph)
+        with pytest.raises(pkg.RadarError) as ei:
+            ring[0].wait()
+        assert ei.value.code == pkg.api.MMW_ERR_STATE
+        got = [None] * F
+        for f in range(F + 2):
+            c = ring[f % 2]
+            if f >= 2:
+                got[f - 2] = c.wait()[0].copy()
+            if f < F:
+                c.set_frame_offset(f)
+                c.submit_host(pinned[f], 1)
+                if f == 0:
+                    with pytest.raises(pkg.RadarError) as ei:
+                        c.submit_host(pinned[f], 1)
+                    assert ei.value.code == pkg.api.MMW_ERR_STATE
+    finally:
+        for c in ring:
+            c.close()
+    assert sum(len(w) for w in want) > 0
+    for f in range(F):
+        assert got[f].tobytes() == want[f].tobytes(), f
