@@ -307,43 +307,65 @@ def run_chain(args, env):
     S, C, A, F, cfg_idx = w["S"], w["C"], w["A"], args.frames or w["F"], w["idx"]
     K, W = args.steps, args.warmup
 
-    ctx = pkg.RadarContext(S, C, A, F, keep_doppler_cube=args.keep_cube, max_det_per_frame=4096, device=env.local_rank)
-    first_frame = rank * F                                     # weak scaling: every rank owns F frames of the global batch
-    ctx.set_frame_offset(first_frame)
-    adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=cfg_idx + 1, first_frame=first_frame)
+    # `inflight` batches in flight: one context + stream + input batch per lane, steps go round-robin over the lanes, so the
+    # tail of one batch's persistent FFT kernels and its latency-bound detection kernels fill with the next batch's work
+    # (profiles/experiments: 1 -> 2 in flight is +10 % on cfg3).  Lane 0 is the one the per-stage numbers are taken from.
+    D = max(1, args.inflight)
+    gather_records = min(F * 4096, 32768)
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    class Lane:
+        def __init__(self, i):
+            self.ctx = pkg.RadarContext(S, C, A, F, keep_doppler_cube=args.keep_cube, max_det_per_frame=4096, device=env.local_rank)
+            first_frame = (i * world + rank) * F              # weak scaling: every rank owns F frames of each global batch
+            self.ctx.set_frame_offset(first_frame)
+            self.adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=cfg_idx + 1, first_frame=first_frame)
+            self.stream = torch.cuda.Stream(device=dev)
+            self.ctx.use_stream(self.stream.cuda_stream)
+            # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel, on a
+            # side stream behind a snapshot of the block so that it overlaps the next step's kernels (sharding.DetectionGather)
+            self.gather = pkg.sharding.DetectionGather(self.ctx, dev, gather_records, side=side) if world > 1 else None
+
+        def step(self):
+            with torch.cuda.stream(self.stream):
+                self.ctx.process_device(self.adc, F)
+                if self.gather is not None:
+                    self.gather.run()
+
+        def flush(self):
+            if self.gather is not None:
+                with torch.cuda.stream(self.stream):
+                    self.gather.flush()
+
+    lanes = [Lane(i) for i in range(D)]
+    ctx, adc, gather = lanes[0].ctx, lanes[0].adc, lanes[0].gather
     torch.cuda.synchronize()
-    stream = torch.cuda.Stream(device=dev)
-    ctx.use_stream(stream.cuda_stream)
     dense_ptr, header_ptr = ctx.device_results()
     header_view = pkg.sharding.device_bytes_view(header_ptr, 16, dev)
-    # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel, on a
-    # side stream behind a snapshot of the block so that it overlaps the next step's kernels (sharding.DetectionGather)
-    gather_records = min(F * ctx.max_det_per_frame, 32768)
-    gather = pkg.sharding.DetectionGather(ctx, dev, gather_records) if world > 1 else None
 
-    def step():
-        ctx.process_device(adc, F)
-        if gather is not None:
-            gather.run()
-
-    with torch.cuda.stream(stream):
-        for _ in range(W):
-            step()
-        if gather is not None:
-            gather.flush()
-        env.sync_all()
-        sampler = ClockSampler(env.local_rank)
-        if rank == 0:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(K):
-            step()
-        if gather is not None:
-            gather.flush()                                  # the last step's gather + merge are inside the timed region
-        e1.record(stream)
-        env.sync_all()
-        ms = e0.elapsed_time(e1)
+    for k in range(max(W, D)):
+        lanes[k % D].step()
+    for ln in lanes:
+        ln.flush()
+    env.sync_all()
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lanes[0].stream)
+    for ln in lanes[1:]:
+        ln.stream.wait_event(e0)
+    for k in range(K):
+        lanes[k % D].step()
+    for ln in lanes:
+        ln.flush()                                          # the last steps' gather + merge are inside the timed region
+    for ln in lanes[1:]:
+        ev = torch.cuda.Event()
+        ev.record(ln.stream)
+        lanes[0].stream.wait_event(ev)
+    e1.record(lanes[0].stream)
+    env.sync_all()
+    ms = e0.elapsed_time(e1)
     ms_by_rank = env.all_ranks(ms)
     ms = max(ms_by_rank)
     frame_counts = ctx.read_counts(F)                       # true per-frame hit counts of this rank's last batch
@@ -401,6 +423,8 @@ def run_chain(args, env):
                 "workload": f"{workload_text(args.workload)}, 2-D CA-CFAR (guard 2x2, train 8x4, alpha 15), "
                             f"{ctx.n_theta}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
                 "frames_per_gpu_per_step": F,
+                "batches_in_flight": D,
+                "ms_per_step_one_in_flight": total_ms / iters,
                 "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel on a side stream, overlapping the next step (overflow={gather_overflow})"),
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
                 "l2": f"inputs larger than L2: {F * 4 * N_adc / 1e6:.0f} MB int16 capture + {F * 8 * A * ctx.Sp * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
@@ -426,7 +450,9 @@ def run_chain(args, env):
             "clocks": clocks,
         }
         if args.workload == "cfg3" and world == 1 and not args.no_other:
-            ctx.close()
+            for ln in lanes:
+                ln.ctx.close()
+                ln.adc = None
             del adc
             torch.cuda.empty_cache()
             line["other_workloads"] = {"cfg2": quick_chain(env, "cfg2")}
@@ -441,7 +467,8 @@ def run_chain(args, env):
                                     "sample": f"{n} frames ({port.pool.shape[0]} distinct, {passes} passes) of the same workload in {dt:.1f} s; "
                                               f"plain-C fp64 oracle (the reference has no CPU code for these stages), {port.cores} OpenMP threads"}
         env.emit(line)
-    ctx.close()
+    for ln in lanes:
+        ln.ctx.close()
 
 
 def run_stream(args, env):
@@ -673,6 +700,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames (cfg5: sensors) per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="cfg3: skip the side measurement of cfg2 (configs[1])")
+    ap.add_argument("--inflight", type=int, default=2, help="cfg2/cfg3/cfg4: batches in flight (contexts on their own streams, steps round-robin)")
     ap.add_argument("--no-graph", action="store_true", help="cfg5: launch the kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--keep-cube", action="store_true", help="materialise the Doppler cube in HBM (default: fused)")
     args = ap.parse_args()

@@ -90,7 +90,7 @@ class DetectionGather:
     receive and merged buffers are double-buffered; flush() makes the compute stream wait for the last exchange.
     The context's stream must be torch's current stream when run() is called."""
 
-    def __init__(self, ctx, device, records_per_rank: int, group=None):
+    def __init__(self, ctx, device, records_per_rank: int, group=None, side=None):
         import torch
         import torch.distributed as dist
 
@@ -104,7 +104,8 @@ class DetectionGather:
         self.local = device_bytes_view(block, self.stride, device)
         self.send = [torch.empty(self.stride, dtype=torch.uint8, device=device) for _ in range(2)]
         self.merged_cap = self.world * records_per_rank
-        self.side = torch.cuda.Stream(device=device)
+        # several gathers (one per batch in flight) must share ONE side stream: NCCL calls on a communicator stay in issue order
+        self.side = side if side is not None else torch.cuda.Stream(device=device)
         self.snap = [torch.cuda.Event() for _ in range(2)]       # snapshot k is in send[k]
         self.done = [None, None]                                   # exchange that last used buffer pair k has finished
         self.step = 0
