@@ -139,6 +139,35 @@ def test_cfar_geometries(pkg, orc, guard, train, alpha):
             assert abs(d["noise"] - by[k]["noise"]) <= 1e-3 * by[k]["noise"] + 1e-7 * ref["P"][k[0]].max()
 
 
+@pytest.mark.parametrize("variant", [1, 22, 42, 82, 23, 43, 83, 24, 44, 84])
+def test_cfar_kernel_forms_agree_with_oracle(pkg, orc, cases, variant, monkeypatch):
+    """Every compiled form of K3 for the default geometry — the tiled kernel (1) and the walk kernel with 64- / 128- /
+    256-bin strips (2 / 3 / 4) and Doppler segments of 32 / 64 / 128 bins (+ 10 * nchunk) — against the oracle: same mask
+    away from threshold cells, and the noise estimate of every detection (the fp32 power map itself differs from the
+    fp64 one by more than the kernels differ from each other: profiles/sweep_k3.py compares the forms directly, 4e-7)."""
+    shape = (256, 128, 4)
+    S, C, A = shape
+    F, adc, wr, wd, ref = cases[shape]
+    near = _near_threshold(ref, 15.0)
+    monkeypatch.setenv("MMW_K3_VARIANT", str(variant))
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        dets, overflow = ctx.process_host(adc, F)
+        masks = [ctx.cfar_mask(f) for f in range(F)]
+    for f in range(F):
+        assert not ((masks[f] != ref["mask"][f]) & ~near[f]).any()
+        for edge in (np.r_[0:12], np.r_[S - 12:S]):                      # clamped range rows; all Doppler columns incl. the wrap
+            assert not ((masks[f][edge] != ref["mask"][f][edge]) & ~near[f][edge]).any()
+    by = {(int(d["frame"]), int(d["range_bin"]), int(d["doppler_bin"])): d for d in ref["dets"]}
+    assert len(dets) > 0 and not overflow
+    hit = 0
+    for d in dets:
+        k = (int(d["frame"]), int(d["range_bin"]), int(d["doppler_bin"]))
+        if k in by:
+            hit += 1
+            assert abs(d["noise"] - by[k]["noise"]) <= 1e-3 * by[k]["noise"] + TOL * 1e-3 * ref["P"][k[0]].max()
+    assert hit >= len(dets) - int(near.sum())
+
+
 def test_detection_list_overflow_is_ordered_and_counted(pkg, orc):
     S, C, A, F = 64, 64, 2, 3
     rng = np.random.default_rng(5)
