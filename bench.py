@@ -328,15 +328,20 @@ def run_chain(args, env):
 
         def step(self):
             with torch.cuda.stream(self.stream):
+                t0 = time.perf_counter()
                 self.ctx.process_device(self.adc, F)
+                t1 = time.perf_counter()
                 if self.gather is not None:
                     self.gather.run()
+                host_split[0] += t1 - t0
+                host_split[1] += time.perf_counter() - t1
 
         def flush(self):
             if self.gather is not None:
                 with torch.cuda.stream(self.stream):
                     self.gather.flush()
 
+    host_split = [0.0, 0.0]                                # host seconds inside process_device / inside the exchange's run()
     lanes = [Lane(i) for i in range(D)]
     ctx, adc, gather = lanes[0].ctx, lanes[0].adc, lanes[0].gather
     torch.cuda.synchronize()
@@ -355,6 +360,7 @@ def run_chain(args, env):
     e0.record(lanes[0].stream)
     for ln in lanes[1:]:
         ln.stream.wait_event(e0)
+    host_split[0] = host_split[1] = 0.0
     t_host = time.perf_counter()
     for k in range(K):
         lanes[k % D].step()
@@ -432,6 +438,7 @@ def run_chain(args, env):
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
                 "l2": f"inputs larger than L2: {F * 4 * N_adc / 1e6:.0f} MB int16 capture + {F * 8 * A * ctx.Sp * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
                 "ms_per_step_by_rank": [m / K for m in ms_by_rank], "host_issue_ms_per_step_by_rank": [m / K for m in host_ms_by_rank],
+                "host_issue_split_ms_per_step_rank0": {"process_device": host_split[0] / K * 1e3, "exchange": host_split[1] / K * 1e3},
                 "rank0_numa_node": env.numa,
                 "detections_per_step": n_det_step, "max_detections_in_one_frame": int(frame_counts.max()),
                 "max_det_per_frame": ctx.max_det_per_frame,
