@@ -684,12 +684,14 @@ def run_legacy(args, env):
                        "l2": f"inputs larger than L2: {F * 204800 / 1e6:.0f} MB of captures per step",
                        "dropin_cudaProcessing_frames_per_s": n_drop / t_drop,
                        "dropin_note": "the reference's own calling pattern: one synchronous cudaProcessing() per 200 KB frame (cudaBenchMarking.cpp:374-378)"},
-            "roofline": {"bound": "hbm", "kernel": "legacy_frame_kernel", "achieved": alg * F * K / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "legacy_cluster_kernel", "achieved": alg * F * K / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg * F * K / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg * F,
-                         "note": "one 16 384-point FFT per frame inside one SM's shared memory: shared-memory/issue bound, not HBM bound (only rx0, 1/4 of the capture, is read)"},
-            "e2e": {"value": world * n_host * e2e_steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": n_host * 204800,
-                    "d2h_bytes_per_step": n_host * 4, "steps": e2e_steps, "api": "mmw_legacy_process_frames"},
+                         "note": "one 16 384-point FFT per frame in the shared memory of an 8-CTA cluster: shared-memory/issue bound, not HBM bound (only rx0, 1/4 of the capture, is read)"},
+            "e2e": {"value": world * n_host * e2e_steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": n_host * 51200,
+                    "d2h_bytes_per_step": n_host * 4, "steps": e2e_steps,
+                    "api": "mmw_legacy_process_frames (pinned host captures of 204 800 B per frame; one strided DMA uploads rx0's rows, "
+                           "the 51 200 B per frame this chain reads)"},
             "gpu_launches": K, "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -41,28 +41,33 @@ constexpr int kSearch = 6553;                      // floor(0.4 * 16384), accele
 constexpr int kFrameShorts = kS * kC * kA * 2;     // 102 400
 constexpr int kNT = 512;
 constexpr int kMaxCand = 32;
+constexpr int kRowShorts = 2 * kS;                 // rx0's I/Q of one chirp: the only part of a frame this chain reads
+constexpr int kFullRowShorts = kA * 2 * kS;        // one chirp of all receivers in the capture
+constexpr int kPackedFrameShorts = kC * kRowShorts;   // 25 600: what the host path uploads per frame (a quarter of the capture)
 
 __device__ __forceinline__ int phys(int i) { return i + (i >> 5); }   // one pad slot per 32: conflict-free in all three passes
 
 struct LegacyArgs {
-    const int16_t *frames;      // [n][kFrameShorts]
+    const int16_t *frames;      // [n][frame_stride]: chirp rows of row_stride shorts, rx0's 2 * kS shorts first in each row
     const double2 *base;        // [kValid]
     const float2 *tw;           // [kN] exp(-2 pi i k / kN)
     float2 *spectrum;           // [kN] of the LAST frame of the launch, or nullptr
     int *raw;                   // [n]
-    int size;                   // valid shorts per frame
+    int size;                   // valid shorts per frame, counted in the capture layout ([chirp][rx][sample], kFrameShorts per frame)
+    int row_stride;             // kA * 2 * kS for frames in the capture layout, 2 * kS for the packed rx0 rows the host path uploads
+    int frame_stride;           // shorts between frames
 };
 
 __device__ __forceinline__ void load_sample(const LegacyArgs &a, const int16_t *frame, int n, double &re, double &im)
 {
-    // rx0 of chirp c, sample s sits at element c*(kA*kS) + s of the [chirp][rx][sample] stream (acceleration.cu:117-150)
+    // rx0 of chirp c, sample s sits at element c*(kA*kS) + s of the [chirp][rx][sample] stream (acceleration.cu:117-150),
+    // i.e. at short c * (kA * 2 * kS) + 4 * (s >> 1) + (s & 1) (and + 2 for Q) of the IIQQ-packed frame
     const int c = n / kS, s = n - c * kS;
-    const int e = c * (kA * kS) + s;
-    const int g = 4 * (e >> 1) + (e & 1);
+    const int in_row = 4 * (s >> 1) + (s & 1);
     double i16 = 0, q16 = 0;
-    if (g + 2 < a.size) {
-        i16 = (double)frame[g];
-        q16 = (double)frame[g + 2];
+    if (c * (kA * 2 * kS) + in_row + 2 < a.size) {
+        i16 = (double)frame[c * a.row_stride + in_row];
+        q16 = (double)frame[c * a.row_stride + in_row + 2];
     }
     const double2 b = a.base[n];
     re = i16 - b.x;
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(kNT, 1) legacy_frame_kernel(LegacyArgs a)
     __shared__ unsigned long long best_key_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int16_t *frame = a.frames + (size_t)blockIdx.x * kFrameShorts;
+    const int16_t *frame = a.frames + (size_t)blockIdx.x * a.frame_stride;
     const bool last = blockIdx.x == gridDim.x - 1;
 
     // ---- gather rx0, subtract the base frame, zero-pad (acceleration.cu:152-166 with the CPU path's padding) ----
@@ -227,12 +232,255 @@ __global__ void __launch_bounds__(kNT, 1) legacy_frame_kernel(LegacyArgs a)
 }
 
 // ---------------------------------------------------------------------------
+// The same frame on a thread-block cluster of 8 CTAs (8 SMs, distributed shared memory): 16 384 = 8 x 2048, decimation in
+// time.  CTA q gathers the samples n = 8 m + q (1/8 of the unpack, base subtraction and conversion work), runs a
+// 2048-point FFT (8 x 16 x 16 register butterflies) in its own shared memory and leaves Y_q[k2] * W_N^(q k2) there; after one
+// cluster barrier CTA j reads its 256 values of k2 from all eight CTAs over DSMEM and finishes with the radix-8 butterfly
+// X[k2 + 2048 k1] = sum_q W_8^(q k1) Y_q[k2] W_N^(q k2), arg-max included.  The per-CTA maxima and the near-tie candidates meet
+// in CTA 0's shared memory; the fp64 re-check of near ties (rare) is CTA 0's.  One frame takes ~1/4 of the single-CTA kernel's time.
+// ---------------------------------------------------------------------------
+constexpr int kCl = 8;                    // CTAs per cluster = frames are split 8 ways
+constexpr int kN2 = kN / kCl;             // 2048-point FFT per CTA
+constexpr int kNTc = 256;
+__device__ __forceinline__ int phys16(int i) { return i + (i >> 4); }   // one pad slot per 16: conflict-free runs of 16 in the last pass
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a shared-memory object of this CTA) in CTA `rank` of the cluster, as a shared::cluster address
+__device__ __forceinline__ uint32_t dsmem_addr(const void *p, uint32_t rank)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float2 dsmem_ld_f2(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long dsmem_ld_u64(uint32_t addr)
+{
+    unsigned long long v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsmem_st_u64(uint32_t addr, unsigned long long v)
+{
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_atom_inc(uint32_t addr)
+{
+    uint32_t old;
+    asm volatile("atom.shared::cluster.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+    return old;
+}
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kNTc, 1) legacy_cluster_kernel(LegacyArgs a)
+{
+    __shared__ __align__(16) float2 sm[kN2 + kN2 / 16];        // the CTA's 2048-point transform, padded
+    __shared__ __align__(16) float2 yb[kN2];                   // Y_q[k2] W_N^(q k2), natural order: read by the whole cluster
+    __shared__ unsigned long long red_key[kNTc / 32];
+    __shared__ unsigned long long cta_keys[kCl];               // CTA 0's copy collects the eight maxima
+    __shared__ double red_d[2][kNTc / 32];
+    __shared__ int cand[kMaxCand];
+    __shared__ int n_cand;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t q = cluster_ctarank();
+    const int fidx = blockIdx.x / kCl;
+    const int16_t *frame = a.frames + (size_t)fidx * a.frame_stride;
+    const bool last = fidx == (int)(gridDim.x / kCl) - 1;
+
+    // ---- gather x[8 m + q]: rx0, minus the base frame, zero-padded ----
+    for (int m = tid; m < kN2; m += kNTc) {
+        const int n = kCl * m + (int)q;
+        float2 v = make_float2(0.f, 0.f);
+        if (n < kValid) {
+            double re, im;
+            load_sample(a, frame, n, re, im);
+            v = make_float2((float)re, (float)im);
+        }
+        sm[phys16(m)] = v;
+    }
+    if (tid == 0) n_cand = 0;
+    __syncthreads();
+
+    // ---- pass 1: 256 radix-8 butterflies, stride 256 ----
+    {
+        const int j = tid;
+        float2 x[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) x[m] = sm[phys16(j + 256 * m)];
+        dft_regs<8>(x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float2 v = x[bitrev(k, 3)];
+            if (k > 0) v = cmul(v, a.tw[kCl * j * k]);                 // W_2048^(j k)
+            sm[phys16(j + 256 * k)] = v;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: 8 blocks x 16 radix-16 butterflies, stride 16 ----
+    if (tid < 128) {
+        const int blk = tid >> 4, j = tid & 15;
+        float2 x[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[m] = sm[phys16(blk * 256 + j + 16 * m)];
+        dft_regs<16>(x);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float2 v = x[bitrev(k, 4)];
+            if (k > 0) v = cmul(v, a.tw[64 * j * k]);                  // W_256^(j k)
+            sm[phys16(blk * 256 + j + 16 * k)] = v;
+        }
+    }
+    __syncthreads();
+    // ---- pass 3: 128 radix-16 butterflies on contiguous runs; k2 = q1 + 8 q2 + 128 q3; times the cluster twiddle W_N^(q k2) ----
+    if (tid < 128) {
+        const int q1 = tid >> 4, q2 = tid & 15;
+        float2 x[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[m] = sm[tid * 17 + m];
+        dft_regs<16>(x);
+#pragma unroll
+        for (int q3 = 0; q3 < 16; ++q3) {
+            const int k2 = q1 + 8 * q2 + 128 * q3;
+            float2 v = x[bitrev(q3, 4)];
+            if (q > 0) v = cmul(v, a.tw[(int)q * k2]);                  // q k2 < 8 * 2048 = kN
+            yb[k2] = v;
+        }
+    }
+    cluster_sync_all();
+
+    // ---- radix-8 across the cluster: this CTA finishes k2 in [256 q, 256 q + 256) ----
+    float mag[4];
+    unsigned long long key = 0;
+    {
+        const int k2 = 256 * (int)q + tid;
+        float2 x[8];
+#pragma unroll
+        for (int r = 0; r < kCl; ++r) x[r] = dsmem_ld_f2(dsmem_addr(&yb[k2], (uint32_t)r));
+        dft_regs<8>(x);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+            const float2 v = x[bitrev(k1, 3)];
+            const int k = k2 + kN2 * k1;
+            if (a.spectrum != nullptr && last) a.spectrum[k] = v;
+            if (k1 < 4) {
+                const float m2 = v.x * v.x + v.y * v.y;
+                mag[k1] = m2;
+                if (k < kSearch) {
+                    const unsigned long long kk = ((unsigned long long)__float_as_uint(m2) << 32) | (unsigned)(0xffffffffu - (unsigned)k);
+                    key = kk > key ? kk : key;
+                }
+            }
+        }
+    }
+    // arg-max: larger power wins, equal power -> smaller bin (first maximum, strict >); CTA, then cluster
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if (lane == 0) red_key[warp] = key;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = 0;
+        for (int w = 0; w < kNTc / 32; ++w) b = red_key[w] > b ? red_key[w] : b;
+        dsmem_st_u64(dsmem_addr(&cta_keys[q], 0), b);
+    }
+    cluster_sync_all();
+    unsigned long long best_key = 0;
+#pragma unroll
+    for (int r = 0; r < kCl; ++r) {
+        const unsigned long long kk = dsmem_ld_u64(dsmem_addr(&cta_keys[r], 0));
+        best_key = kk > best_key ? kk : best_key;
+    }
+    const float best_m = __uint_as_float((unsigned)(best_key >> 32));
+    int best_k = (int)(0xffffffffu - (unsigned)(best_key & 0xffffffffu));
+    if (best_key == 0ull) best_k = 0;
+
+    // ---- near ties: every bin within 1e-4 of the fp32 maximum goes to CTA 0's candidate list ----
+    {
+        const float thr = best_m * (1.0f - 1e-4f);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            const int k = 256 * (int)q + tid + kN2 * k1;
+            if (k < kSearch && best_m > 0.f && mag[k1] >= thr) {
+                const uint32_t slot = dsmem_atom_inc(dsmem_addr(&n_cand, 0));
+                if (slot < (uint32_t)kMaxCand) dsmem_st_u32(dsmem_addr(&cand[slot], 0), (uint32_t)k);
+            }
+        }
+    }
+    cluster_sync_all();
+    if (q != 0) return;                                        // nothing reads the other CTAs' shared memory any more
+
+    const int nc = n_cand;
+    if (nc > 1 && nc <= kMaxCand) {
+        if (tid == 0) {                                   // ascending bin order
+            for (int i = 1; i < nc; ++i) {
+                const int v = cand[i];
+                int j = i - 1;
+                while (j >= 0 && cand[j] > v) { cand[j + 1] = cand[j]; --j; }
+                cand[j + 1] = v;
+            }
+        }
+        __syncthreads();
+        double best64 = 0.0;
+        int best64_k = 0;
+        for (int ci = 0; ci < nc; ++ci) {
+            const int k = cand[ci];
+            double sr = 0.0, si = 0.0;
+            for (int n = tid; n < kValid; n += kNTc) {
+                double xr, xi, sn, cs;
+                load_sample(a, frame, n, xr, xi);
+                sincospi((double)((k * n) & (kN - 1)) / (double)(kN / 2), &sn, &cs);
+                sr += xr * cs + xi * sn;                   // (xr + j xi)(c - j s)
+                si += xi * cs - xr * sn;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                si += __shfl_xor_sync(0xffffffffu, si, o);
+            }
+            if (lane == 0) { red_d[0][warp] = sr; red_d[1][warp] = si; }
+            __syncthreads();
+            if (tid == 0) {
+                double r = 0, i = 0;
+                for (int w = 0; w < kNTc / 32; ++w) { r += red_d[0][w]; i += red_d[1][w]; }
+                const double m = r * r + i * i;
+                if (m > best64) { best64 = m; best64_k = k; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) a.raw[fidx] = best64_k;
+    } else if (tid == 0) {
+        a.raw[fidx] = best_k;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host state (lazy singleton; the reference API has no init/teardown call)
 // ---------------------------------------------------------------------------
 struct LegacyState {
     bool ready = false;
     cudaStream_t stream = nullptr;
-    int16_t *d_frames = nullptr;
+    int16_t *d_frames = nullptr;   // [frames_cap][kC][kRowShorts]: rx0 rows only
+    int16_t *h_stage = nullptr;    // pinned, same shape: pageable captures are packed here by the CPU (allocated on first use)
+    int stage_cap = 0;
     int frames_cap = 0;
     double2 *d_base = nullptr;
     float2 *d_tw = nullptr;
@@ -265,7 +513,7 @@ cudaError_t ensure_frames(int n)
     if (g.d_raw) cudaFree(g.d_raw);
     if (g.h_raw) cudaFreeHost(g.h_raw);
     g.d_frames = nullptr; g.d_raw = nullptr; g.h_raw = nullptr; g.frames_cap = 0;
-    LCHECK(cudaMalloc(&g.d_frames, (size_t)n * kFrameShorts * sizeof(int16_t)));
+    LCHECK(cudaMalloc(&g.d_frames, (size_t)n * kPackedFrameShorts * sizeof(int16_t)));
     LCHECK(cudaMalloc(&g.d_raw, (size_t)n * sizeof(int)));
     LCHECK(cudaMallocHost(&g.h_raw, (size_t)n * sizeof(int)));
     g.frames_cap = n;
@@ -316,19 +564,54 @@ double distance_from_raw(int raw)
     return lightSpeed * (((double)maxDisIdx / extendedSize) * Fs_extend) / (2 * mu);
 }
 
+cudaError_t launch_frames(const LegacyArgs &a, int n)
+{
+    const char *v = getenv("MMW_LEGACY_VARIANT");          // 1: the single-CTA kernel instead of the 8-CTA cluster (profiles/, tests)
+    if (v && atoi(v) == 1)
+        legacy_frame_kernel<<<n, kNT, kSmemBytes, g.stream>>>(a);
+    else
+        legacy_cluster_kernel<<<n * kCl, kNTc, 0, g.stream>>>(a);
+    return cudaGetLastError();
+}
+
+// Only rx0's rows go up: 51 200 of the frame's 204 800 bytes.  A pinned capture is read by one strided (2-D) DMA; a pageable
+// one (the reference's malloc'ed `input`, cudaBenchMarking.cpp:350) is packed into a pinned staging buffer by the CPU first.
+cudaError_t upload_rx0(const short *frames, int n, int spacing, int per)
+{
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned && per == kFrameShorts && spacing == kFrameShorts) {
+        LCHECK(cudaMemcpy2DAsync(g.d_frames, kRowShorts * sizeof(int16_t), frames, kFullRowShorts * sizeof(int16_t), kRowShorts * sizeof(int16_t),
+                                 (size_t)n * kC, cudaMemcpyHostToDevice, g.stream));
+        return cudaSuccess;
+    }
+    if (n > g.stage_cap) {
+        if (g.h_stage) cudaFreeHost(g.h_stage);
+        g.h_stage = nullptr; g.stage_cap = 0;
+        LCHECK(cudaMallocHost(&g.h_stage, (size_t)n * kPackedFrameShorts * sizeof(int16_t)));
+        g.stage_cap = n;
+    }
+    for (int f = 0; f < n; ++f) {
+        const short *src = frames + (size_t)f * spacing;
+        int16_t *dst = g.h_stage + (size_t)f * kPackedFrameShorts;
+        for (int c = 0; c < kC; ++c) {
+            const int left = per - c * kFullRowShorts;           // valid shorts from the start of this chirp row on
+            if (left <= 0) break;                                // the kernel never reads past `size` (load_sample)
+            memcpy(dst + c * kRowShorts, src + c * kFullRowShorts, (size_t)(left < kRowShorts ? left : kRowShorts) * sizeof(int16_t));
+        }
+    }
+    LCHECK(cudaMemcpyAsync(g.d_frames, g.h_stage, (size_t)n * kPackedFrameShorts * sizeof(int16_t), cudaMemcpyHostToDevice, g.stream));
+    return cudaSuccess;
+}
+
 cudaError_t run_frames(const short *frames, int n, const double *base, int size, bool want_spec)
 {
     LCHECK(ensure_init());
     LCHECK(ensure_frames(n));
     LCHECK(upload_base(base));
     const int per = size < kFrameShorts ? size : kFrameShorts;
-    if (per == kFrameShorts) {
-        LCHECK(cudaMemcpyAsync(g.d_frames, frames, (size_t)n * kFrameShorts * sizeof(int16_t), cudaMemcpyHostToDevice, g.stream));
-    } else {
-        for (int f = 0; f < n; ++f)
-            LCHECK(cudaMemcpyAsync(g.d_frames + (size_t)f * kFrameShorts, frames + (size_t)f * size, (size_t)per * sizeof(int16_t),
-                                   cudaMemcpyHostToDevice, g.stream));
-    }
+    LCHECK(upload_rx0(frames, n, per == kFrameShorts ? kFrameShorts : size, per));
     LegacyArgs a;
     a.frames = g.d_frames;
     a.base = g.d_base;
@@ -336,8 +619,9 @@ cudaError_t run_frames(const short *frames, int n, const double *base, int size,
     a.spectrum = want_spec ? g.d_spec : nullptr;
     a.raw = g.d_raw;
     a.size = per;
-    legacy_frame_kernel<<<n, kNT, kSmemBytes, g.stream>>>(a);
-    LCHECK(cudaGetLastError());
+    a.row_stride = kRowShorts;
+    a.frame_stride = kPackedFrameShorts;
+    LCHECK(launch_frames(a, n));
     LCHECK(cudaMemcpyAsync(g.h_raw, g.d_raw, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
     LCHECK(cudaStreamSynchronize(g.stream));
     return cudaSuccess;
@@ -427,8 +711,9 @@ int mmw_legacy_process_device(const short *frames_dev, int n_frames, const doubl
     a.spectrum = nullptr;
     a.raw = raw_dev;
     a.size = kFrameShorts;
-    legacy_frame_kernel<<<n_frames, kNT, kSmemBytes, g.stream>>>(a);
-    if (cudaGetLastError() != cudaSuccess) {
+    a.row_stride = kFullRowShorts;          // frames in HBM keep the capture layout
+    a.frame_stride = kFrameShorts;
+    if (launch_frames(a, n_frames) != cudaSuccess) {
         mmw::set_last_error("legacy_frame_kernel launch failed");
         return MMW_ERR_CUDA;
     }
@@ -519,7 +804,7 @@ void mmw_legacy_shutdown(void)
     g.ready = false;
     // at process exit the context may already be gone; ignore errors
     cudaFree(g.d_frames); cudaFree(g.d_base); cudaFree(g.d_tw); cudaFree(g.d_spec); cudaFree(g.d_raw);
-    cudaFreeHost(g.h_raw);
+    cudaFreeHost(g.h_raw); cudaFreeHost(g.h_stage);
     if (g.stream) cudaStreamDestroy(g.stream);
     free(g.h_base_copy);
     g = LegacyState();

@@ -237,7 +237,10 @@ def test_user_windows_round_trip(pkg, orc):
 
 
 # ---------------------------------------------------------------- legacy path (reference cfg 100 x 128 x 4)
-def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir):
+@pytest.mark.parametrize("kernel", ["cluster", "single_cta"])
+def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir, kernel, monkeypatch):
+    """both forms of the legacy frame kernel: the 8-CTA cluster (default) and the single-CTA kernel (MMW_LEGACY_VARIANT=1)"""
+    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "0")
     gold = np.load(f"{golden_dir}/legacy_reference.npz")
     i = 0
     timers = np.zeros(4)
@@ -259,7 +262,9 @@ def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir):
     assert timers[3] > 0 and timers[3] >= timers[0] > 0                   # accumulated seconds (+=)
 
 
-def test_legacy_full_spectrum_and_edges(pkg, orc):
+@pytest.mark.parametrize("kernel", ["cluster", "single_cta"])
+def test_legacy_full_spectrum_and_edges(pkg, orc, kernel, monkeypatch):
+    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "0")
     cap = pkg.synth.legacy_capture(3, seed=21)
     base = orc.reshape(cap[0], 100, 128, 4)[:12800]
     d_ref, raw_ref, spec_ref = orc.legacy_frame(cap[2], base, want_spectrum=True)
@@ -280,3 +285,20 @@ def test_legacy_full_spectrum_and_edges(pkg, orc):
     frame = pkg.synth.pack_iiqq(z).reshape(-1)
     zero_base = np.zeros(12800, complex)
     assert pkg.api.legacy_process_frame(frame, zero_base) == orc.legacy_frame(frame, zero_base)
+
+
+def test_legacy_upload_paths_and_short_frames(pkg, orc):
+    """the host path uploads rx0's rows only: a pinned capture by one strided DMA, a pageable one packed by the CPU; frames
+    cut short at any point (inside rx0's row, inside another receiver's, on a row boundary) follow the reference's size rule"""
+    import torch
+
+    cap = pkg.synth.legacy_capture(9, seed=6, moving=True)
+    base = orc.reshape(cap[0], 100, 128, 4)[:12800]
+    want = [orc.legacy_frame(cap[f], base) for f in range(1, 9)]
+    d0, r0 = pkg.api.legacy_process_frames(cap[1:], base)
+    pinned = torch.from_numpy(cap[1:].copy()).pin_memory()
+    d1, r1 = pkg.api.legacy_process_frames(pinned.numpy(), base)
+    assert [(float(d), int(r)) for d, r in zip(d0, r0)] == want
+    assert np.array_equal(d0, d1) and np.array_equal(r0, r1)
+    for size in (102399, 102400 - 600, 64000, 51300, 800 * 17, 800 * 17 + 100, 800 * 17 + 199, 801, 150, 3):
+        assert pkg.api.legacy_process_frame(cap[2][:size], base) == orc.legacy_frame(cap[2][:size], base), size
