@@ -157,6 +157,14 @@ def workload_text(name):
     return f"{name}: {w['S']} samples x {w['C']} chirps x {w['A']} antennas"
 
 
+def chain_workload_text(name):
+    """config.workload of the batched chain: the same string on both arms"""
+    w = WORKLOADS[name]
+    n_theta = 64 if w["A"] <= 64 else 1 << (w["A"] - 1).bit_length()
+    return (f"{workload_text(name)}, 2-D CA-CFAR (guard 2x2, train 8x4, alpha 15), {n_theta}-pt angle FFT "
+            f"(BASELINE.json configs[{w['idx']}])")
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  cfg1: the reference's own
     code (oracle/_ref).  Other workloads: the reference has no CPU (or GPU) code for the range/Doppler/CFAR/angle chain
@@ -188,8 +196,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * T / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.workload) + (", 2-D CA-CFAR, angle FFT" if w["kind"] != "legacy" else "")
-                               + (f" (BASELINE.json configs[{w['idx']}])" if w["kind"] != "legacy" else ""),
+        "config": {"workload": workload_text(args.workload) if w["kind"] == "legacy" else chain_workload_text(args.workload),
                    "frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": used, "kind": kind,
                          "sample": f"{per_step} frames per step x {len(times)} steps, {what}, {used} thread(s)"},
@@ -429,8 +436,7 @@ def run_chain(args, env):
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{workload_text(args.workload)}, 2-D CA-CFAR (guard 2x2, train 8x4, alpha 15), "
-                            f"{ctx.n_theta}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
+                "workload": chain_workload_text(args.workload),
                 "frames_per_gpu_per_step": F,
                 "batches_in_flight": D,
                 "ms_per_step_one_in_flight": total_ms / iters,
@@ -684,10 +690,10 @@ def run_legacy(args, env):
                        "l2": f"inputs larger than L2: {F * 204800 / 1e6:.0f} MB of captures per step",
                        "dropin_cudaProcessing_frames_per_s": n_drop / t_drop,
                        "dropin_note": "the reference's own calling pattern: one synchronous cudaProcessing() per 200 KB frame (cudaBenchMarking.cpp:374-378)"},
-            "roofline": {"bound": "hbm", "kernel": "legacy_cluster_kernel", "achieved": alg * F * K / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "legacy_frame_kernel", "achieved": alg * F * K / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg * F * K / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg * F,
-                         "note": "one 16 384-point FFT per frame in the shared memory of an 8-CTA cluster: shared-memory/issue bound, not HBM bound (only rx0, 1/4 of the capture, is read)"},
+                         "note": "one 16 384-point FFT per frame inside one SM's shared memory (batches; single-frame calls run on an 8-CTA cluster): shared-memory/issue bound, not HBM bound (only rx0, 1/4 of the capture, is read)"},
             "e2e": {"value": world * n_host * e2e_steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": n_host * 51200,
                     "d2h_bytes_per_step": n_host * 4, "steps": e2e_steps,
                     "api": "mmw_legacy_process_frames (pinned host captures of 204 800 B per frame; one strided DMA uploads rx0's rows, "

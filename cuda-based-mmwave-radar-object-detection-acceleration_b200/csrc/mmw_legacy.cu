@@ -485,8 +485,8 @@ struct LegacyState {
     double2 *d_base = nullptr;
     float2 *d_tw = nullptr;
     float2 *d_spec = nullptr;
-    int *d_raw = nullptr;
-    int *h_raw = nullptr;          // pinned
+    int *d_raw = nullptr;          // device alias of h_raw
+    int *h_raw = nullptr;          // pinned, mapped
     int raw_cap = 0;
     double *h_base_copy = nullptr; // last base frame uploaded
     bool base_valid = false;
@@ -510,12 +510,13 @@ cudaError_t ensure_frames(int n)
 {
     if (n <= g.frames_cap) return cudaSuccess;
     if (g.d_frames) cudaFree(g.d_frames);
-    if (g.d_raw) cudaFree(g.d_raw);
     if (g.h_raw) cudaFreeHost(g.h_raw);
     g.d_frames = nullptr; g.d_raw = nullptr; g.h_raw = nullptr; g.frames_cap = 0;
     LCHECK(cudaMalloc(&g.d_frames, (size_t)n * kPackedFrameShorts * sizeof(int16_t)));
-    LCHECK(cudaMalloc(&g.d_raw, (size_t)n * sizeof(int)));
-    LCHECK(cudaMallocHost(&g.h_raw, (size_t)n * sizeof(int)));
+    // the 4-byte result per frame is written by the kernel straight into mapped pinned host memory: no D2H copy on the
+    // single-frame path (one DMA operation less per cudaProcessing() call); stream synchronisation makes it visible
+    LCHECK(cudaHostAlloc(&g.h_raw, (size_t)n * sizeof(int), cudaHostAllocMapped));
+    LCHECK(cudaHostGetDevicePointer(&g.d_raw, g.h_raw, 0));
     g.frames_cap = n;
     return cudaSuccess;
 }
@@ -564,13 +565,19 @@ double distance_from_raw(int raw)
     return lightSpeed * (((double)maxDisIdx / extendedSize) * Fs_extend) / (2 * mu);
 }
 
+// A few frames per launch (the drop-in's one frame per call) are latency-bound: the 8-CTA cluster finishes a frame in about a
+// quarter of the single-CTA kernel's time.  Many frames per launch are throughput-bound, and there one CTA per frame wins
+// (5.0 M against 2.2 M frames/s device-resident: no cluster barriers, no idle half of the CTA in passes 2 and 3); the two
+// lines cross near 60 frames per launch.  MMW_LEGACY_VARIANT = 1 / 2 forces the single-CTA / cluster kernel (profiles/, tests).
 cudaError_t launch_frames(const LegacyArgs &a, int n)
 {
-    const char *v = getenv("MMW_LEGACY_VARIANT");          // 1: the single-CTA kernel instead of the 8-CTA cluster (profiles/, tests)
-    if (v && atoi(v) == 1)
-        legacy_frame_kernel<<<n, kNT, kSmemBytes, g.stream>>>(a);
-    else
+    const char *v = getenv("MMW_LEGACY_VARIANT");
+    const int var = v ? atoi(v) : 0;
+    const bool cluster = var == 2 || (var != 1 && n <= 48);
+    if (cluster)
         legacy_cluster_kernel<<<n * kCl, kNTc, 0, g.stream>>>(a);
+    else
+        legacy_frame_kernel<<<n, kNT, kSmemBytes, g.stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -605,13 +612,17 @@ cudaError_t upload_rx0(const short *frames, int n, int spacing, int per)
     return cudaSuccess;
 }
 
-cudaError_t run_frames(const short *frames, int n, const double *base, int size, bool want_spec)
+// The capture goes on the bus first; comparing the base frame with the one already in HBM (204 800 bytes of host memory,
+// several microseconds) then runs under that DMA.  *t_prepared: host clock once everything before the launch is queued.
+double now_s();
+cudaError_t run_frames(const short *frames, int n, const double *base, int size, bool want_spec, double *t_prepared = nullptr)
 {
     LCHECK(ensure_init());
     LCHECK(ensure_frames(n));
-    LCHECK(upload_base(base));
     const int per = size < kFrameShorts ? size : kFrameShorts;
     LCHECK(upload_rx0(frames, n, per == kFrameShorts ? kFrameShorts : size, per));
+    LCHECK(upload_base(base));
+    if (t_prepared) *t_prepared = now_s();
     LegacyArgs a;
     a.frames = g.d_frames;
     a.base = g.d_base;
@@ -622,8 +633,7 @@ cudaError_t run_frames(const short *frames, int n, const double *base, int size,
     a.row_stride = kRowShorts;
     a.frame_stride = kPackedFrameShorts;
     LCHECK(launch_frames(a, n));
-    LCHECK(cudaMemcpyAsync(g.h_raw, g.d_raw, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-    LCHECK(cudaStreamSynchronize(g.stream));
+    LCHECK(cudaStreamSynchronize(g.stream));             // a.raw is mapped host memory (ensure_frames): the results are in g.h_raw
     return cudaSuccess;
 }
 
@@ -641,11 +651,8 @@ double cudaProcessing(short *input_host, Complex_t *host_baseFrame, int size, do
 {
     std::lock_guard<std::mutex> lk(g_mu);
     const double t0 = now_s();
-    cudaError_t e = ensure_init();
-    if (e == cudaSuccess) e = ensure_frames(1);
-    if (e == cudaSuccess) e = upload_base(reinterpret_cast<const double *>(host_baseFrame));
-    const double t1 = now_s();
-    if (e == cudaSuccess) e = run_frames(input_host, 1, reinterpret_cast<const double *>(host_baseFrame), size, true);
+    double t1 = t0;
+    cudaError_t e = run_frames(input_host, 1, reinterpret_cast<const double *>(host_baseFrame), size, true, &t1);
     if (e != cudaSuccess) {
         // the reference exits silently with the CUDA error code (acceleration.cu:19-31); keep the exit, add the message
         fprintf(stderr, "cudaProcessing: %s\n", mmw_last_error());
@@ -660,8 +667,8 @@ double cudaProcessing(short *input_host, Complex_t *host_baseFrame, int size, do
     // the reference accumulates seconds with += (acceleration.cu:534-537)
     if (totalTime) *totalTime += t3 - t0;
     if (findMaxTime) *findMaxTime += t3 - t2;
-    if (preProcessTime) *preProcessTime += t1 - t0;     // state check + base-frame upload: everything before the fused launch
-    if (fftTime) *fftTime += t3 - t1;                   // H2D + fused kernel (unpack .. FFT .. arg-max) + 4-byte D2H + formula
+    if (preProcessTime) *preProcessTime += t1 - t0;     // rx0 rows packed and queued for upload, base frame checked: everything before the launch
+    if (fftTime) *fftTime += t3 - t1;                   // fused kernel (unpack .. FFT .. arg-max), result read-back, formula
     return maxDis;
 }
 
@@ -803,7 +810,7 @@ void mmw_legacy_shutdown(void)
     if (!g.ready) return;
     g.ready = false;
     // at process exit the context may already be gone; ignore errors
-    cudaFree(g.d_frames); cudaFree(g.d_base); cudaFree(g.d_tw); cudaFree(g.d_spec); cudaFree(g.d_raw);
+    cudaFree(g.d_frames); cudaFree(g.d_base); cudaFree(g.d_tw); cudaFree(g.d_spec);
     cudaFreeHost(g.h_raw); cudaFreeHost(g.h_stage);
     if (g.stream) cudaStreamDestroy(g.stream);
     free(g.h_base_copy);

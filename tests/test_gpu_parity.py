@@ -240,7 +240,7 @@ def test_user_windows_round_trip(pkg, orc):
 @pytest.mark.parametrize("kernel", ["cluster", "single_cta"])
 def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir, kernel, monkeypatch):
     """both forms of the legacy frame kernel: the 8-CTA cluster (default) and the single-CTA kernel (MMW_LEGACY_VARIANT=1)"""
-    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "0")
+    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "2")
     gold = np.load(f"{golden_dir}/legacy_reference.npz")
     i = 0
     timers = np.zeros(4)
@@ -264,7 +264,7 @@ def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir, kernel, monkeypa
 
 @pytest.mark.parametrize("kernel", ["cluster", "single_cta"])
 def test_legacy_full_spectrum_and_edges(pkg, orc, kernel, monkeypatch):
-    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "0")
+    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "2")
     cap = pkg.synth.legacy_capture(3, seed=21)
     base = orc.reshape(cap[0], 100, 128, 4)[:12800]
     d_ref, raw_ref, spec_ref = orc.legacy_frame(cap[2], base, want_spectrum=True)
