@@ -25,3 +25,10 @@ with tempfile.TemporaryDirectory() as d:
         print("\n".join(l for l in r.stdout.splitlines() if "Inner CUDA" not in l))
         if r.stderr.strip():
             print("stderr:", r.stderr.strip()[:500])
+
+probe = os.path.join(ROOT, "profiles", "tools", "init_probe")          # g++ -O2 init_probe.cpp (see its header), run from the repo root
+if os.path.exists(probe):
+    print("\n===== profiles/tools/init_probe (same box): where the first call's time goes =====")
+    for rep in range(2):
+        r = subprocess.run([probe], cwd=ROOT, capture_output=True, text=True, timeout=600)
+        print(r.stdout.strip() + ("   (second process on the box)" if rep else ""))
