@@ -553,7 +553,7 @@ def run_stream(args, env):
     lat_us = np.sort(np.array(lat)) * 1e6
     # the same calls split in two (mmw_submit_host / mmw_wait) over a ring of contexts: `depth` frames in flight, the upload
     # of frame k+1 under the kernels and read-back of frame k
-    depth = 2
+    depth = max(1, args.depth)
     ring = [pkg.RadarContext(S, C, A, 1, max_det_per_frame=4096, device=env.local_rank) for _ in range(depth)]
     for c in ring:
         c.set_graph_mode(not args.no_graph)
@@ -720,6 +720,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="cfg3: skip the side measurement of cfg2 (configs[1])")
     ap.add_argument("--inflight", type=int, default=3, help="cfg2/cfg3/cfg4: batches in flight (contexts on their own streams, steps round-robin)")
+    ap.add_argument("--depth", type=int, default=4, help="cfg5: one-frame calls in flight on the end-to-end path (ring of contexts, mmw_submit_host / mmw_wait)")
     ap.add_argument("--no-graph", action="store_true", help="cfg5: launch the kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--keep-cube", action="store_true", help="materialise the Doppler cube in HBM (default: fused)")
     args = ap.parse_args()

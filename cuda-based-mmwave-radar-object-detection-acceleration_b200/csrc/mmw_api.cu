@@ -466,6 +466,10 @@ static int check_batch_args(mmw_ctx *c, const void *adc, int n_frames, const cha
         set_last_error("%s: n_frames %d outside 1..max_frames(%d)", who, n_frames, c->cfg.max_frames);
         return MMW_ERR_ARG;
     }
+    if (c->submitted) {         // the context's buffers belong to the batch queued by mmw_submit_host until mmw_wait collects it
+        set_last_error("%s: a batch submitted with mmw_submit_host has not been collected with mmw_wait", who);
+        return MMW_ERR_STATE;
+    }
     return MMW_OK;
 }
 
@@ -572,7 +576,6 @@ int mmw_submit_host(mmw_ctx *c, const int16_t *adc_host, int n_frames)
 {
     int rc = check_batch_args(c, adc_host, n_frames, "mmw_submit_host");
     if (rc) return rc;
-    if (c->submitted) { set_last_error("mmw_submit_host: the previous batch has not been collected with mmw_wait"); return MMW_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     rc = run_host_batch(c, adc_host, n_frames);
     if (rc) return rc;
@@ -601,6 +604,7 @@ int mmw_process_capture_file(mmw_ctx *c, const char *path, long long first_frame
     if (n_frames_done) *n_frames_done = 0;
     if (!c || !path) { set_last_error("mmw_process_capture_file: null argument"); return MMW_ERR_ARG; }
     if (first_frame < 0 || det_capacity < 0 || (det_capacity > 0 && !dets)) { set_last_error("mmw_process_capture_file: bad argument"); return MMW_ERR_ARG; }
+    if (c->submitted) { set_last_error("mmw_process_capture_file: a submitted batch is pending; collect it with mmw_wait"); return MMW_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     const size_t frame_shorts = (size_t)2 * c->plan.S * c->plan.C * c->plan.A;
     const size_t frame_bytes = frame_shorts * sizeof(int16_t);
@@ -712,6 +716,7 @@ int mmw_read_detections(mmw_ctx *c, mmw_detection *dets, int det_capacity, int *
 {
     if (!c) { set_last_error("mmw_read_detections: null context"); return MMW_ERR_ARG; }
     if (c->last_frames <= 0) { set_last_error("mmw_read_detections: no batch processed"); return MMW_ERR_STATE; }
+    if (c->submitted) { set_last_error("mmw_read_detections: a submitted batch is pending; collect it with mmw_wait"); return MMW_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     return fetch_results(c, dets, det_capacity, n_det);
 }

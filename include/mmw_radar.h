@@ -133,7 +133,9 @@ int mmw_process_host(mmw_ctx *ctx, const int16_t *adc_host, int n_frames,
  * each with its own stream): mmw_submit_host queues the upload, the chain and the read-back of the result block and
  * returns without waiting; mmw_wait blocks until that batch is done and hands out its detections.  The capture buffer
  * must stay valid until mmw_wait returns and should be pinned (a pageable buffer makes the upload synchronous).
- * One batch per context at a time: a second submit before the wait returns MMW_ERR_STATE. */
+ * One batch per context at a time: between a submit and its wait, a second submit and every other call that would run or
+ * read a batch on this context (mmw_process_device, mmw_time_device, mmw_read_detections, mmw_process_capture_file) return
+ * MMW_ERR_STATE. */
 int mmw_submit_host(mmw_ctx *ctx, const int16_t *adc_host, int n_frames);
 int mmw_wait(mmw_ctx *ctx, mmw_detection *dets, int det_capacity, int *n_det);
 

@@ -210,9 +210,11 @@ def test_submit_wait_two_batches_in_flight(pkg, batches, graph):
                 c.set_frame_offset(f)
                 c.submit_host(pinned[f], 1)
                 if f == 0:
-                    with pytest.raises(pkg.RadarError) as ei:
-                        c.submit_host(pinned[f], 1)
-                    assert ei.value.code == pkg.api.MMW_ERR_STATE
+                    for call in (lambda: c.submit_host(pinned[f], 1), lambda: c.read_detections(),
+                                 lambda: c.process_device(torch.zeros(c.frame_shorts, dtype=torch.int16, device="cuda"), 1)):
+                        with pytest.raises(pkg.RadarError) as ei:
+                            call()
+                        assert ei.value.code == pkg.api.MMW_ERR_STATE
     finally:
         for c in ring:
             c.close()
