@@ -64,3 +64,25 @@ def test_cxx_host_program_against_the_c_abi(pkg, tmp_path):
     assert f"b200 detections {len(want)}," in r.stdout and "(9 frames" in r.stdout and "range " in r.stdout
     r = subprocess.run([str(exe), str(tmp_path / "missing.bin"), str(S), str(C), str(A)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 1 and "unable to read the specified file" in r.stdout
+
+
+def test_cxx_streaming_program(pkg, tmp_path):
+    """examples/b200_stream.cpp: the per-frame loop over mmw_submit_host / mmw_wait with a ring of contexts; every depth
+    gives the detection count of the batched in-memory path"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "b200_stream"
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    r = subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-Wall", "-Werror", "-o", str(exe), os.path.join(root, "examples", "b200_stream.cpp"),
+                        "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"), pkg.api.library_path(),
+                        "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.dirname(pkg.api.library_path())],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    S, C, A = 256, 128, 12
+    adc = pkg.synth.cube_batch(11, S, C, A, cfg=5, n_targets=4)
+    adc.tofile(tmp_path / "cap.bin")
+    with pkg.RadarContext(S, C, A, 11) as ctx:
+        want, _ = ctx.process_host(adc, 11)
+    for depth in (1, 2, 4):
+        r = subprocess.run([str(exe), str(tmp_path / "cap.bin"), str(S), str(C), str(A), str(depth)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert f"b200 stream detections {len(want)} in 11 frames" in r.stdout, r.stdout
