@@ -302,3 +302,35 @@ def test_legacy_upload_paths_and_short_frames(pkg, orc):
     assert np.array_equal(d0, d1) and np.array_equal(r0, r1)
     for size in (102399, 102400 - 600, 64000, 51300, 800 * 17, 800 * 17 + 100, 800 * 17 + 199, 801, 150, 3):
         assert pkg.api.legacy_process_frame(cap[2][:size], base) == orc.legacy_frame(cap[2][:size], base), size
+
+
+def test_chain_matches_numpy_golden_fixture(pkg, golden_dir):
+    """the CUDA chain against tests/golden/chain_numpy.npz — numbers produced by numpy alone (make_chain_golden.py), not by the
+    oracle: power map within 1e-4 of its maximum, hit cells exactly away from threshold cells, angle bins away from ties"""
+    g = np.load(f"{golden_dir}/chain_numpy.npz")
+    for (S, C, A, F, cfg) in [tuple(int(v) for v in row) for row in g["cases"]]:
+        tag = f"{S}x{C}x{A}"
+        adc = pkg.synth.cube_batch(F, S, C, A, cfg=cfg, n_targets=4)
+        with pkg.RadarContext(S, C, A, F) as ctx:
+            Sp, Cp = ctx.Sp, ctx.Cp
+            dets, overflow = ctx.process_host(adc, F)
+            assert not overflow
+            for f in range(F):
+                P = g[f"P_{tag}_f{f}"]
+                assert relmax(ctx.power_map(f), P) < TOL
+                mask = np.unpackbits(g[f"mask_{tag}_f{f}"])[: Sp * Cp].reshape(Sp, Cp).astype(bool)
+                near = np.unpackbits(g[f"near_{tag}_f{f}"])[: Sp * Cp].reshape(Sp, Cp).astype(bool)
+                got = ctx.cfar_mask(f).astype(bool)
+                assert np.array_equal(got[~near], mask[~near])
+                by = {(int(d["range_bin"]), int(d["doppler_bin"])): d for d in dets[dets["frame"] == f]}
+                n_checked = 0
+                for (r, d), nz, ab, tie in zip(g[f"hits_{tag}_f{f}"], g[f"noise_at_hits_{tag}_f{f}"], g[f"angle_bin_{tag}_f{f}"],
+                                               g[f"angle_tie_{tag}_f{f}"]):
+                    if near[r, d]:
+                        continue
+                    rec = by[(int(r), int(d))]
+                    assert abs(rec["noise"] - nz) <= 1e-3 * nz + TOL * 1e-3 * P.max()
+                    if not tie:
+                        assert rec["angle_bin"] == ab
+                    n_checked += 1
+                assert n_checked > 0

@@ -150,3 +150,38 @@ def test_empty_and_ragged_inputs(orc):
     full = orc.process_frames(adc, 1, S, C, A, orc.hann_periodic(S), orc.hann_periodic(C), alpha=1.5)
     cut = orc.process_frames(adc, 1, S, C, A, orc.hann_periodic(S), orc.hann_periodic(C), alpha=1.5, det_cap_per_frame=7)
     assert full["n_total"] > 7 and cut["n_total"] == full["n_total"] and np.array_equal(cut["dets"], full["dets"][:7])
+
+
+def _chain_golden_cases(golden_dir):
+    g = np.load(f"{golden_dir}/chain_numpy.npz")
+    return g, [tuple(int(v) for v in row) for row in g["cases"]]
+
+
+def test_oracle_matches_numpy_golden_fixture(orc, pkg, golden_dir):
+    """tests/golden/chain_numpy.npz (numpy.fft + brute-force sums, generated without oracle code) pins the oracle's
+    north-star stages: power map to 1e-12, hit cells exactly away from threshold, angle bins away from ties, peak flags."""
+    import hashlib
+
+    g, cases = _chain_golden_cases(golden_dir)
+    for (S, C, A, F, cfg) in cases:
+        tag = f"{S}x{C}x{A}"
+        adc = pkg.synth.cube_batch(F, S, C, A, cfg=cfg, n_targets=4)
+        assert hashlib.sha256(adc.tobytes()).digest() == g[f"adc_sha256_{tag}"].tobytes()      # the synthetic input is reproducible
+        Sp, Cp = orc.next_pow2(S), orc.next_pow2(C)
+        out = orc.process_frames(adc, F, S, C, A, orc.hann_periodic(S), orc.hann_periodic(C), want=("P", "mask", "noise"))
+        for f in range(F):
+            P = g[f"P_{tag}_f{f}"]
+            assert np.abs(out["P"][f] - P).max() <= 1e-12 * P.max()
+            mask = np.unpackbits(g[f"mask_{tag}_f{f}"])[: Sp * Cp].reshape(Sp, Cp).astype(bool)
+            near = np.unpackbits(g[f"near_{tag}_f{f}"])[: Sp * Cp].reshape(Sp, Cp).astype(bool)
+            assert np.array_equal(out["mask"][f].astype(bool)[~near], mask[~near])
+            dets = out["dets"][out["dets"]["frame"] == f]
+            by = {(int(d["range_bin"]), int(d["doppler_bin"])): d for d in dets}
+            for (r, d), nz, ab, tie, pk in zip(g[f"hits_{tag}_f{f}"], g[f"noise_at_hits_{tag}_f{f}"], g[f"angle_bin_{tag}_f{f}"],
+                                               g[f"angle_tie_{tag}_f{f}"], g[f"peak_{tag}_f{f}"]):
+                if near[r, d]:
+                    continue
+                rec = by[(int(r), int(d))]
+                assert abs(rec["noise"] - nz) <= 1e-6 * nz and bool(rec["flags"] & 1) == bool(pk)
+                if not tie:
+                    assert rec["angle_bin"] == ab
