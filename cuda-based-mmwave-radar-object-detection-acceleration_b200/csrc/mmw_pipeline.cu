@@ -65,7 +65,7 @@ struct RangeSmem {
 // few MB read by every CTA); reading them with per-lane global loads instead costs 4x sector over-fetch and +70 % time.
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE>
 __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
-                                                            int n_tiles)
+                                                            int n_tiles, int l2_ahead)
 {
     static_assert(R1 * R2 == N, "plan");
     using L = RangeSmem<N, BT, NSTAGE, BASE>;
@@ -109,6 +109,17 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
         }
     };
 
+    // The staging copy of a tile is issued one tile ahead and has only the second FFT pass to land (ncu: a third of the warp
+    // samples sit on the mbarrier wait).  Its rows are therefore pulled into L2 `l2_ahead` tiles earlier with a bulk prefetch
+    // hint (no shared memory, nothing to wait for), so that the staging copy itself is an L2 hit.
+    auto prefetch = [&](int tile) {         // one warp
+        const int ct = tile % nct, fa = tile / nct;
+        const int a = fa % A, f = fa / A;
+        const int c0 = ct * BT;
+        if (lane < min(BT, C - c0))
+            bulk_prefetch_l2(adc + (((size_t)f * C + c0 + lane) * A + a) * (size_t)(2 * S), (uint32_t)(S * 4));
+    };
+
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -117,6 +128,9 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
     __syncthreads();
     int tile = blockIdx.x;
     if (warp == 0 && tile < n_tiles) issue(tile, 0);
+    if (warp == 1 && l2_ahead > 0)
+        for (int j = 1; j <= l2_ahead; ++j)
+            if (tile + j * (int)gridDim.x < n_tiles) prefetch(tile + j * (int)gridDim.x);
     for (int i = tid; i < N; i += NT) tw[i] = p.tw1_r[i];
     for (int i = tid; i < N; i += NT) win[i] = i < S ? p.win_r[i] : 0.f;
     __syncthreads();
@@ -215,6 +229,7 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
         // soon as the last warp has pulled its pass-1 inputs into registers — removes the wait on the copy but not a
         // microsecond of run time: the stall moves to the barrier, profiles/experiments/r1_k1_early_release.md.)
         if (NSTAGE == 1 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
+        if (warp == 1 && l2_ahead > 0 && tile + (l2_ahead + 1) * (int)gridDim.x < n_tiles) prefetch(tile + (l2_ahead + 1) * (int)gridDim.x);
 
         // ---- pass 2: R1 butterflies of radix R2 on contiguous runs; outputs go straight to HBM ----
         float2 *out = rs + (size_t)fa * (size_t)N * C + c0 + row;
@@ -677,6 +692,8 @@ static cudaError_t resident_ctas(K kernel, int threads, int smem_bytes, int *cta
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, threads, smem_bytes);
 }
 
+constexpr int kRangeL2Ahead = 0;       // default look-ahead of K1's L2 prefetch hints (tiles)
+
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE = false>
 static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
@@ -692,7 +709,8 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
     const int nct = (p.C + BT - 1) / BT;
     const long long tiles = (long long)n_frames * p.A * nct;
     const int grid = (int)(tiles < (long long)per_sm * sm_count() ? tiles : (long long)per_sm * sm_count());
-    k<<<grid, NW * 32, bytes, st>>>(p, adc, rs, (int)tiles);
+    const char *la = getenv("MMW_K1_L2_AHEAD");                        // tiles of L2 look-ahead (0 = off; profiles/sweep_variants.py)
+    k<<<grid, NW * 32, bytes, st>>>(p, adc, rs, (int)tiles, la ? atoi(la) : kRangeL2Ahead);
     return cudaGetLastError();
 }
 
