@@ -692,6 +692,15 @@ static cudaError_t resident_ctas(K kernel, int threads, int smem_bytes, int *cta
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, threads, smem_bytes);
 }
 
+// MMW_CTAS_PER_SM (experiment): cap of resident CTAs per SM for the persistent FFT kernels, so that the FFT kernels of two
+// batches in flight can share every SM instead of taking turns (profiles/experiments/r1_fft_corun.log)
+static int capped_per_sm(int per_sm)
+{
+    const char *e = getenv("MMW_CTAS_PER_SM");
+    const int cap = e ? atoi(e) : 0;
+    return cap > 0 && cap < per_sm ? cap : per_sm;
+}
+
 constexpr int kRangeL2Ahead = 0;       // default look-ahead of K1's L2 prefetch hints (tiles)
 
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE = false>
@@ -708,7 +717,7 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
     }
     const int nct = (p.C + BT - 1) / BT;
     const long long tiles = (long long)n_frames * p.A * nct;
-    const int grid = (int)(tiles < (long long)per_sm * sm_count() ? tiles : (long long)per_sm * sm_count());
+    const int grid = (int)(tiles < (long long)capped_per_sm(per_sm) * sm_count() ? tiles : (long long)capped_per_sm(per_sm) * sm_count());
     const char *la = getenv("MMW_K1_L2_AHEAD");                        // tiles of L2 look-ahead (0 = off; profiles/sweep_variants.py)
     k<<<grid, NW * 32, bytes, st>>>(p, adc, rs, (int)tiles, la ? atoi(la) : kRangeL2Ahead);
     return cudaGetLastError();
@@ -746,7 +755,7 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     const long long tiles = (long long)n_frames * (p.Sp / BT);
-    const int grid = (int)(tiles < (long long)per_sm * sm_count() ? tiles : (long long)per_sm * sm_count());
+    const int grid = (int)(tiles < (long long)capped_per_sm(per_sm) * sm_count() ? tiles : (long long)capped_per_sm(per_sm) * sm_count());
     k<<<grid, NW * 32, bytes, st>>>(p, rs, cube, pmap, (int)tiles);
     return cudaGetLastError();
 }
@@ -766,7 +775,7 @@ static cudaError_t run_doppler_warp_t(const PlanDev &p, const float2 *rs, float 
     }
     const long long tiles = (long long)n_frames * (p.Sp / L::kRows);
     const long long want = (tiles + NW - 1) / NW;
-    const int grid = (int)(want < (long long)per_sm * sm_count() ? want : (long long)per_sm * sm_count());
+    const int grid = (int)(want < (long long)capped_per_sm(per_sm) * sm_count() ? want : (long long)capped_per_sm(per_sm) * sm_count());
     k<<<grid, NW * 32, bytes, st>>>(p, rs, pmap, (int)tiles);
     return cudaGetLastError();
 }

@@ -13,9 +13,11 @@ import __graft_entry__ as entry  # noqa: E402
 pkg = entry.load_package()
 SHAPES = {"cfg3": (512, 256, 12, 64), "cfg2": (256, 128, 4, 1024), "cfg5": (256, 128, 12, 64)}
 dev = torch.device("cuda", 0)
-for wl in (sys.argv[1:] or ["cfg3", "cfg2"]):
+CAPS = [int(c) for c in os.environ.get("PROBE_CAPS", "0").split(",")]      # MMW_CTAS_PER_SM values to try (0 = no cap)
+for wl, cap in [(w, c) for w in (sys.argv[1:] or ["cfg3", "cfg2"]) for c in CAPS]:
     S, C, A, F = SHAPES[wl]
-    for depth in (1, 2, 3):
+    os.environ["MMW_CTAS_PER_SM"] = str(cap)
+    for depth in (1, 2, 3, 4):
         ctxs = [pkg.RadarContext(S, C, A, F) for _ in range(depth)]
         adcs = [pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=3, first_frame=i * F) for i in range(depth)]
         K = 30
@@ -27,7 +29,7 @@ for wl in (sys.argv[1:] or ["cfg3", "cfg2"]):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         n = [len(c.read_detections()[0]) for c in ctxs]
-        print(f"{wl} in flight {depth}: {dt / K * 1e3:.4f} ms per batch, {F * K / dt:.0f} frames/s, detections {n}", flush=True)
+        print(f"{wl} ctas/SM cap {cap} in flight {depth}: {dt / K * 1e3:.4f} ms per batch, {F * K / dt:.0f} frames/s, detections {n}", flush=True)
         for c in ctxs:
             c.close()
         del adcs
