@@ -1,8 +1,11 @@
 // mmw_detect.cu — stages 3 and 4 of the chain: power map -> detection records.
 //
-//   K3  cfar_kernel     2-D cell-averaging CFAR on the integrated power map.  Range axis clamps
+//   K3  cfar_walk_kernel / cfar_kernel
+//                       2-D cell-averaging CFAR on the integrated power map.  Range axis clamps
 //                       (training count recounted), Doppler axis wraps.  Emits a bit mask and, for
-//                       hit cells only, the noise estimate.
+//                       hit cells only, the noise estimate.  Default geometry: the "walk" form (Doppler
+//                       sums in registers down each range column, range sums on packed pairs out of
+//                       shared memory); any other guard / training window: the tiled kernel.
 //   K4a list_kernel     per frame: ordered compaction of the mask bits into (range, doppler) keys and
 //                       the per-frame count; the last CTA to finish scans the counts into offsets of
 //                       the dense list and writes the header (no extra launch, no host round trip).
@@ -16,9 +19,10 @@
 // Numerical note on the CFAR sums.  A target cell is up to ~1e9 x the noise floor after the 2-D FFT
 // gain, so running sums with subtraction, prefix-sum differences and "outer box minus inner box" are
 // all unusable in fp32: they leave an error of tens of noise floors behind every strong cell.  Every
-// sum below therefore only ever ADDS training cells: per row a `full` window sum and a `ring` sum
-// (full minus the guard span, computed as left + right), then a column sum that takes `ring` rows
-// inside the Doppler guard and `full` rows outside it.
+// sum below therefore only ever ADDS training cells.  Tiled kernel: per row a `full` window sum and a
+// `ring` sum (full minus the guard span, computed as left + right), then a column sum that takes `ring`
+// rows inside the Doppler guard and `full` rows outside it; the walk kernel splits the window the other
+// way round (see its header).
 #include <stdlib.h>
 
 #include "mmw_common.cuh"

@@ -3,9 +3,13 @@
 // The reference runs, per 200 KB frame, 6 cudaMalloc + 6 cudaFree + 5 cudaMemcpy + 4 device syncs
 // + 19 launches (unpack, reshape, extension, bit reversal, 14 global-memory radix-2 stages) and then
 // copies the whole fp64 spectrum back to search it on the host.  Here one frame is ONE launch of
-// ONE kernel: rx0 gather + int16 unpack + base-frame subtraction + zero pad + a 16 384-point FFT held
-// entirely in one SM's shared memory (16 x 32 x 32 register butterflies) + the arg-max, with 4 bytes
-// going back to the host.  Device state is created once and reused.
+// ONE kernel: rx0 gather + int16 unpack + base-frame subtraction + zero pad + a 16 384-point FFT + the
+// arg-max, with 4 bytes going back to the host (into mapped pinned memory: no copy).  Batches run one
+// CTA per frame with the FFT held entirely in one SM's shared memory (16 x 32 x 32 register
+// butterflies, legacy_frame_kernel); a single frame per call — the reference's calling pattern — runs
+// on a thread-block cluster of 8 CTAs that exchange their partial spectra over distributed shared
+// memory (legacy_cluster_kernel).  Only rx0's rows of a capture are uploaded.  Device state is created
+// once and reused.
 //
 // Numerics: the FFT runs in fp32 (inputs are int16 differences, exactly representable).  So that the
 // returned distance is the reference's even when two bins are within fp32 rounding of each other,
