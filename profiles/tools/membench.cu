@@ -24,6 +24,37 @@ __global__ void k_copy(const int4 *__restrict__ in, int4 *__restrict__ out, size
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
+// K1's traffic mix: one byte read for two written.  Contiguous form: 16 B in, 32 B out per thread and step.
+__global__ void k_mix12(const int4 *__restrict__ in, int4 *__restrict__ out, size_t n_in)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_in; i += (size_t)gridDim.x * blockDim.x) {
+        int4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + i));
+        out[2 * i] = v;
+        out[2 * i + 1] = v;
+    }
+}
+// K1's store pattern: the corner-turned range spectrum [slab][range 512][chirp 256] float2 is written in pieces of 16 chirps
+// (128 B) per range row, 2 KB apart; the 16 pieces of a row come from 16 different CTAs (consecutive tiles) at about the same
+// time.  A CTA = one tile (slab, chirp block): reads its 32 KB of "ADC" contiguously, then writes 512 x 128 B at stride 2 KB
+// with 8-byte stores (lanes 0-15 one row, lanes 16-31 the next), as the kernel does.
+__global__ void k_mix12_k1pattern(const int4 *__restrict__ in, float2 *__restrict__ out, size_t n_tiles)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const size_t slab = t / 16, cb = t % 16;
+        int4 acc = make_int4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) {            // 32 KB in
+            int4 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + t * 2048 + i));
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+        const float2 val = make_float2(__int_as_float(acc.x ^ acc.z), __int_as_float(acc.y ^ acc.w));
+        float2 *o = out + slab * (512 * 256) + cb * 16 + (lane & 15);
+        for (int r = 2 * warp + (lane >> 4); r < 512; r += 2 * nw)          // 64 KB out
+            asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(o + (size_t)r * 256), "f"(val.x), "f"(val.y) : "memory");
+    }
+}
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // each CTA streams CHUNK-byte pieces through a 2-deep ring of shared-memory buffers with cp.async.bulk
 template <int CHUNK>
@@ -89,6 +120,16 @@ int main()
         time("read  LDG.128", (double)bytes, [&] { k_read<<<blocks, 512>>>((const int4 *)a, n, (int4 *)b); });
         time("write STG.128", (double)bytes, [&] { k_write<<<blocks, 512>>>((int4 *)b, n); });
         time("copy  (read+write bytes)", 2.0 * bytes, [&] { k_copy<<<blocks, 512>>>((const int4 *)a, (int4 *)b, n); });
+    }
+    for (int blocks : {148 * 4, 148 * 8}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "1 read : 2 write, contiguous, %d", blocks);
+        time(nm, 1.5 * bytes, [&] { k_mix12<<<blocks, 512>>>((const int4 *)a, (int4 *)b, n / 2); });
+    }
+    for (int per_sm : {2, 4, 8}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "1 : 2, K1 store pattern, %d/SM", per_sm);
+        time(nm, 1.5 * bytes, [&] { k_mix12_k1pattern<<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 65536); });
     }
     cudaFuncSetAttribute(k_tma_read<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(k_tma_read<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
