@@ -824,12 +824,24 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     case 64:   return run_range<64, 8, 8, 16, 4, true, 0, 0>(p, adc, rs, n_frames, st);
     case 128:  return run_range<128, 8, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
     // double-buffered staging (NSTAGE = 2) and BT = 8 tiles were measured slower for 256 and 512 points
-    // (profiles/experiments/r1_k1_variants_sweep.log); the single-buffer BT = 16 shape stays
-    case 256:  return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
-    case 512:  return run_range<512, 16, 32, 16, 8, true, 256, 0, 1, 8, 4>(p, adc, rs, n_frames, st);
-    // 1024 points: a 16-row tile needs 209 KB (one CTA per SM); 8 rows fit two CTAs per SM and measured 2.4 % faster
-    // (profiles/experiments/r1_cfg4_tile_sweep.log)
-    case 1024: return run_range<1024, 32, 32, 8, 8, false, 512, 0, 1, 4, 4>(p, adc, rs, n_frames, st);
+    // (profiles/experiments/r1_k1_variants_sweep.log)
+    // Tile height = bytes per range row in one corner-turned store: a 1 : 2 read:write mover reaches 5.2 TB/s with 128-byte pieces
+    // and 5.6-5.7 TB/s with 256-byte ones (profiles/membench_r1.txt).  256 points: 32-row tiles still fit two CTAs of 8 warps per SM
+    // and measured 4.5 % faster than 16-row tiles with three CTAs of 4 warps (cfg2 0.293 -> 0.280 ms).  512 points: a 32-row tile
+    // needs 203 KB, one CTA of 16 warps per SM, and loses more to the barrier between the passes than the stores gain (0.224 ->
+    // 0.238 ms).  MMW_K1_VARIANT = 5 / 6 force 32- / 16-row tiles (profiles/experiments/r1_k1_tile_height.log).
+    case 256:
+        if (variant("MMW_K1_VARIANT") == 6) return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
+        return run_range<256, 16, 16, 32, 8, true, 128, 0, 1, 16, 4>(p, adc, rs, n_frames, st);
+    case 512:
+        if (variant("MMW_K1_VARIANT") == 5) return run_range<512, 16, 32, 32, 16, true, 256, 0, 1, 8, 4>(p, adc, rs, n_frames, st);
+        return run_range<512, 16, 32, 16, 8, true, 256, 0, 1, 8, 4>(p, adc, rs, n_frames, st);
+    // 1024 points: a 16-row tile needs 209 KB (one CTA per SM).  With 8 warps it lost 2.4 % to 8-row tiles at two CTAs per SM
+    // (profiles/experiments/r1_cfg4_tile_sweep.log); with 16 warps it wins 1-4 % (64-byte store pieces are the worst case of
+    // profiles/membench_r1.txt: 4.2 TB/s), profiles/experiments/r1_k1_tile_height.log.  MMW_K1_VARIANT = 6: the 8-row shape.
+    case 1024:
+        if (variant("MMW_K1_VARIANT") == 6) return run_range<1024, 32, 32, 8, 8, false, 512, 0, 1, 4, 4>(p, adc, rs, n_frames, st);
+        return run_range<1024, 32, 32, 16, 16, false, 512, 0, 1, 4, 4>(p, adc, rs, n_frames, st);
     default:   return cudaErrorInvalidValue;
     }
 }

@@ -24,14 +24,14 @@ __global__ void k_copy(const int4 *__restrict__ in, int4 *__restrict__ out, size
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
-// K1's traffic mix: one byte read for two written.  Contiguous form: 16 B in, 32 B out per thread and step.
+// K1's traffic mix: one byte read for two written.  Contiguous form: 16 B in, 2 x 16 B out (two coalesced streams) per thread and step.
 __global__ void k_mix12(const int4 *__restrict__ in, int4 *__restrict__ out, size_t n_in)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_in; i += (size_t)gridDim.x * blockDim.x) {
         int4 v;
         asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + i));
-        out[2 * i] = v;
-        out[2 * i + 1] = v;
+        out[i] = v;                      // two fully coalesced output streams
+        out[i + n_in] = v;
     }
 }
 // K1's store pattern: the corner-turned range spectrum [slab][range 512][chirp 256] float2 is written in pieces of 16 chirps
@@ -53,6 +53,31 @@ __global__ void k_mix12_k1pattern(const int4 *__restrict__ in, float2 *__restric
         float2 *o = out + slab * (512 * 256) + cb * 16 + (lane & 15);
         for (int r = 2 * warp + (lane >> 4); r < 512; r += 2 * nw)          // 64 KB out
             asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(o + (size_t)r * 256), "f"(val.x), "f"(val.y) : "memory");
+    }
+}
+// the same traffic with wider pieces per range row: PIECE chirps (PIECE * 8 bytes) per row, i.e. what a tile of PIECE chirps would store
+template <int PIECE>
+__global__ void k_mix12_rows(const int4 *__restrict__ in, float2 *__restrict__ out, size_t n_tiles)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    constexpr int BLOCKS = 256 / PIECE;                                   // tiles per slab
+    constexpr int IN16 = PIECE * 512 * 4 / 16;                            // int4 per tile (PIECE chirps x 512 samples x 4 B)
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const size_t slab = t / BLOCKS, cb = t % BLOCKS;
+        int4 acc = make_int4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < IN16; i += blockDim.x) {
+            int4 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + t * IN16 + i));
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+        const float2 val = make_float2(__int_as_float(acc.x ^ acc.z), __int_as_float(acc.y ^ acc.w));
+        constexpr int LPR = PIECE < 32 ? PIECE : 32;                      // lanes per row piece
+        constexpr int RPW = 32 / LPR;                                     // rows per warp store
+        float2 *o = out + slab * (512 * 256) + cb * PIECE + (lane % LPR);
+        for (int r = RPW * warp + lane / LPR; r < 512; r += RPW * nw)
+#pragma unroll
+            for (int c = 0; c < PIECE; c += 32)
+                asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(o + (size_t)r * 256 + c), "f"(val.x), "f"(val.y) : "memory");
     }
 }
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,6 +155,19 @@ int main()
         char nm[64];
         snprintf(nm, sizeof nm, "1 : 2, K1 store pattern, %d/SM", per_sm);
         time(nm, 1.5 * bytes, [&] { k_mix12_k1pattern<<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 65536); });
+    }
+    for (int per_sm : {4, 8}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "1 : 2, 64 B pieces, %d/SM", per_sm);
+        time(nm, 1.5 * bytes, [&] { k_mix12_rows<8><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 32768); });
+        snprintf(nm, sizeof nm, "1 : 2, 128 B pieces, %d/SM", per_sm);
+        time(nm, 1.5 * bytes, [&] { k_mix12_rows<16><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 65536); });
+        snprintf(nm, sizeof nm, "1 : 2, 256 B pieces, %d/SM", per_sm);
+        time(nm, 1.5 * bytes, [&] { k_mix12_rows<32><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 131072); });
+        snprintf(nm, sizeof nm, "1 : 2, 512 B pieces, %d/SM", per_sm);
+        time(nm, 1.5 * bytes, [&] { k_mix12_rows<64><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 262144); });
+        snprintf(nm, sizeof nm, "1 : 2, whole 2 KB rows, %d/SM", per_sm);
+        time(nm, 1.5 * bytes, [&] { k_mix12_rows<256><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 1048576); });
     }
     cudaFuncSetAttribute(k_tma_read<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(k_tma_read<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
