@@ -453,7 +453,8 @@ def run_chain(args, env):
                 "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "note": "peak is the 1:1 copy figure of MEASURED_PEAKS.json; a bare data mover with this kernel's 1 : 2 read:write mix reaches "
-                        "4.9 TB/s (contiguous) to 5.26 TB/s (this kernel's store pattern) on a B200 of this pool (profiles/membench_r1.txt)",
+                        "5.75 TB/s with contiguous stores and 5.2 TB/s with 128-byte corner-turned pieces like this kernel's at 512 points "
+                        "(profiles/membench_r1.txt)",
                 "algorithmic_bytes_per_launch": stage_bytes[dom], "kernel_ms": stage_ms[dom],
                 "stage_ms": dict(zip(names, stage_ms)),
                 "stage_gbs": {n: (b / (t * 1e-3) / 1e9 if t > 0 else None) for n, b, t in zip(names, stage_bytes, stage_ms)},

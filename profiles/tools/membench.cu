@@ -115,6 +115,50 @@ __global__ void k_tma_read(const char *__restrict__ in, size_t nchunks, int *sin
     if (acc == 0x12345678) sink[0] = acc;
 }
 
+// K2's loads if the range spectrum were stored tile-contiguously ([slab][chirp block of 16][range 512][16 chirps]): a range row of
+// 256 chirps = 16 pieces of 128 B, 64 KB apart.  Warp-private staging as in doppler_fft_warp_kernel: a warp stages two rows
+// (32 pieces, one bulk copy per lane) per step through a 2-deep ring.  PIECES = 1: today's layout (one 2 KB copy per row).
+template <int PIECES>
+__global__ void k_tma_rows(const char *__restrict__ in, size_t n_rows, int *sink)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ uint64_t bar[8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) {
+        for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar[warp][b])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncwarp();
+    unsigned char *mine = sm + warp * 2 * 4096;
+    constexpr int PB = 2048 / PIECES;                                  // bytes per piece
+    auto issue = [&](size_t pair, int st) {                              // rows 2 pair, 2 pair + 1
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&bar[warp][st & 1])), "r"(4096));
+        __syncwarp();
+        for (int i = lane; i < 2 * PIECES; i += 32) {
+            const size_t row = 2 * pair + i / PIECES, slab = row / 512, r = row % 512;
+            const int piece = i % PIECES;
+            // tiled layout: [slab][piece][r][PB bytes]; PIECES = 1 degenerates to [slab][r][2048]
+            const char *src = in + slab * (512 * 2048) + (size_t)piece * (512 * PB) + r * PB;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(mine + (st & 1) * 4096 + i * PB)),
+                         "l"(src), "r"(PB), "r"(s32(&bar[warp][st & 1])));
+        }
+    };
+    const size_t n_pairs = n_rows / 2, stride = (size_t)gridDim.x * nw;
+    size_t pair = (size_t)blockIdx.x * nw + warp;
+    int acc = 0, s = 0;
+    if (pair < n_pairs) issue(pair, 0);
+    for (; pair < n_pairs; pair += stride, ++s) {
+        if (pair + stride < n_pairs) issue(pair + stride, s + 1);
+        uint32_t done;
+        do {
+            asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p;}" : "=r"(done) : "r"(s32(&bar[warp][s & 1])), "r"((s >> 1) & 1));
+        } while (!done);
+        acc ^= reinterpret_cast<const int *>(mine + (s & 1) * 4096)[lane * 32];
+        __syncwarp();
+    }
+    if (acc == 0x12345678) sink[0] = acc;
+}
+
 int main()
 {
     const size_t bytes = 2048ull << 20;
@@ -168,6 +212,18 @@ int main()
         time(nm, 1.5 * bytes, [&] { k_mix12_rows<64><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 262144); });
         snprintf(nm, sizeof nm, "1 : 2, whole 2 KB rows, %d/SM", per_sm);
         time(nm, 1.5 * bytes, [&] { k_mix12_rows<256><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 1048576); });
+    }
+    cudaFuncSetAttribute(k_tma_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(k_tma_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(k_tma_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    for (int per_sm : {2, 3}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "read rows, 1 x 2 KB, %d/SM", per_sm);
+        time(nm, (double)bytes, [&] { k_tma_rows<1><<<148 * per_sm, 256, 65536>>>(a, bytes / 2048, (int *)b); });
+        snprintf(nm, sizeof nm, "read rows, 8 x 256 B, %d/SM", per_sm);
+        time(nm, (double)bytes, [&] { k_tma_rows<8><<<148 * per_sm, 256, 65536>>>(a, bytes / 2048, (int *)b); });
+        snprintf(nm, sizeof nm, "read rows, 16 x 128 B, %d/SM", per_sm);
+        time(nm, (double)bytes, [&] { k_tma_rows<16><<<148 * per_sm, 256, 65536>>>(a, bytes / 2048, (int *)b); });
     }
     cudaFuncSetAttribute(k_tma_read<32768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(k_tma_read<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
