@@ -80,6 +80,25 @@ __global__ void k_mix12_rows(const int4 *__restrict__ in, float2 *__restrict__ o
                 asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(o + (size_t)r * 256 + c), "f"(val.x), "f"(val.y) : "memory");
     }
 }
+// 16-chirp tiles storing into a range spectrum tiled by 32 chirps ([slab][chirp/32][range 512][32]): 128-byte halves of adjacent
+// 256-byte pieces, the other half coming from the neighbouring tile (another CTA)
+__global__ void k_mix12_tiled32(const int4 *__restrict__ in, float2 *__restrict__ out, size_t n_tiles)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const size_t slab = t / 16, cb = t % 16;
+        int4 acc = make_int4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+            int4 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(in + t * 2048 + i));
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+        const float2 val = make_float2(__int_as_float(acc.x ^ acc.z), __int_as_float(acc.y ^ acc.w));
+        float2 *o = out + slab * (512 * 256) + (cb >> 1) * (512 * 32) + (cb & 1) * 16 + (lane & 15);
+        for (int r = 2 * warp + (lane >> 4); r < 512; r += 2 * nw)
+            asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(o + (size_t)r * 32), "f"(val.x), "f"(val.y) : "memory");
+    }
+}
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // each CTA streams CHUNK-byte pieces through a 2-deep ring of shared-memory buffers with cp.async.bulk
 template <int CHUNK>
@@ -212,6 +231,11 @@ int main()
         time(nm, 1.5 * bytes, [&] { k_mix12_rows<64><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 262144); });
         snprintf(nm, sizeof nm, "1 : 2, whole 2 KB rows, %d/SM", per_sm);
         time(nm, 1.5 * bytes, [&] { k_mix12_rows<256><<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 1048576); });
+    }
+    for (int per_sm : {2, 4, 8}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "1 : 2, 128 B into 32-tiled, %d/SM", per_sm);
+        time(nm, 1.5 * bytes, [&] { k_mix12_tiled32<<<148 * per_sm, 256>>>((const int4 *)a, (float2 *)b, bytes / 65536); });
     }
     cudaFuncSetAttribute(k_tma_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(k_tma_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
