@@ -27,6 +27,7 @@ struct PlanDev {
     const float2 *tw1_d;    // [Cp]  pass-1 twiddles of the Doppler FFT in consumption order
     const float2 *tw_a;     // [n_theta]
     const int16_t *base_adc; // one frame [C][A][S] IIQQ subtracted before the range window, or nullptr (static-clutter removal)
+    int k2_last_frame_first; // K2 walks the batch from its last frame to its first: the range spectrum K1 wrote last is still in L2
 };
 
 // internal HBM layouts

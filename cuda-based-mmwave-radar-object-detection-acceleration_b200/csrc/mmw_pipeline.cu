@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
         const long long tl = (long long)blockIdx.x + (long long)itq * gridDim.x;
         if (tl >= n_tiles) return;
         const int tile = (int)tl;
-        const int rt = tile % nrt, f = tile / nrt;
+        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
         const int buf = q % NSTAGE;
         uint64_t *b = &bar[buf];
         if (lane == 0) {
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
 
 #pragma unroll 1
     for (; tile < n_tiles; tile += gridDim.x) {
-        const int rt = tile % nrt, f = tile / nrt;
+        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
         const int r0 = rt * BT;
         float acc[UPS2][R2];
 #pragma unroll
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p,
         const long long tl = gw + (long long)itq * nwarp;
         if (tl >= n_tiles) return;
         const int tile = (int)tl;
-        const int rt = tile % nrt, f = tile / nrt;
+        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
         uint64_t *b = &bar[q % NSTAGE];
         if (lane == 0) {
             fence_proxy_async();
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p,
 #pragma unroll 1
     for (long long tl = gw; tl < n_tiles; tl += nwarp) {
         const int tile = (int)tl;
-        const int rt = tile % nrt, f = tile / nrt;
+        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
         float acc[U2][R2];
 #pragma unroll
         for (int u = 0; u < U2; ++u)
@@ -701,7 +701,8 @@ static int capped_per_sm(int per_sm)
     return cap > 0 && cap < per_sm ? cap : per_sm;
 }
 
-constexpr int kRangeL2Ahead = 0;       // default look-ahead of K1's L2 prefetch hints (tiles)
+constexpr int kRangeL2Ahead = 0;
+constexpr int kK2LastFrameFirst = 0;   // default order of K2 over the frames of a batch       // default look-ahead of K1's L2 prefetch hints (tiles)
 
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE = false>
 static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
@@ -846,8 +847,13 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     }
 }
 
-cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
+cudaError_t launch_doppler_fft(const PlanDev &plan, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
+    PlanDev p = plan;
+    {   // MMW_K2_REVERSE = 0: first frame first (profiles/experiments/r1_k2_frame_order.log)
+        const char *e = getenv("MMW_K2_REVERSE");
+        p.k2_last_frame_first = e ? atoi(e) : kK2LastFrameFirst;
+    }
     switch (p.Cp) {
     case 64:   return run_doppler<64, 8, 8, 16, 4, 0, 0>(p, rs, cube, pmap, n_frames, st);
     case 128: {
