@@ -286,52 +286,62 @@ class Env:
             self.dist.destroy_process_group()
 
 
-def quick_chain(env, name, steps=10):
-    """device-resident frames/s of another chain workload, measured the same way (CUDA events, batch larger than L2); a
-    side note in the default line so that configs[1] is on record next to the headline configuration"""
-    torch, pkg, dev = env.torch, env.pkg, env.dev
-    w = WORKLOADS[name]
-    S, C, A, F = w["S"], w["C"], w["A"], w["F"]
-    ctx = pkg.RadarContext(S, C, A, F, max_det_per_frame=4096, device=env.local_rank)
-    adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=w["idx"] + 1)
-    torch.cuda.synchronize()
-    ctx.time_device(adc, F, 3)
-    total_ms, stage_ms = ctx.time_device(adc, F, steps, per_stage=True)
-    info = {"workload": f"{workload_text(name)} (BASELINE.json configs[{w['idx']}])", "frames_per_gpu_per_step": F, "steps": steps,
-            "value": F * steps / (total_ms * 1e-3), "unit": "frames/s", "ms_per_step": total_ms / steps,
-            "stage_ms": dict(zip(["range_fft_kernel", "doppler_fft_kernel", "cfar_kernel", "list_kernel+measure_kernel"], [x / steps for x in stage_ms])),
-            "pipeline_frac_of_measured_hbm_peak": int(ctx.info.algorithmic_bytes_per_frame) * F * steps / (total_ms * 1e-3) / 1e9 / peaks()[0]}
-    ctx.close()
-    del adc
-    torch.cuda.empty_cache()
-    return info
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at the workload's bench batch size, read from the
+    newest committed `ncu --set full` capture of that workload (profiles/ncu_rN_stages_<workload>_raw.csv, written by
+    profiles/ncu_stage_table.py).  Returns (bytes, file name) or (None, None) when no capture names that kernel."""
+    import csv
+    import glob
+    import re
+
+    best = None
+    for path in glob.glob(os.path.join(ROOT, "profiles", f"ncu_r*_stages_{workload}_raw.csv")):
+        m = re.search(r"ncu_r(\d+)_stages_", os.path.basename(path))
+        if m and (best is None or int(m.group(1)) > best[0]):
+            best = (int(m.group(1)), path)
+    if best is None:
+        return None, None
+    rows = list(csv.reader(open(best[1])))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    want = kernel.split("+")[0]
+    for r in rows[2:]:
+        if want in r[ix["Kernel Name"]]:
+            tot = sum(float(r[ix[k]]) * scale[units[ix[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            return int(tot), os.path.relpath(best[1], ROOT)
+    return None, None
 
 
-def run_chain(args, env):
-    """cfg2 / cfg3 / cfg4: batches through the whole chain"""
+STAGE_NAMES = ["range_fft_kernel", "doppler_fft_kernel", "cfar_kernel", "list_kernel+measure_kernel"]
+# per-frame detection capacity the bench gives each workload (the dense imaging scene of cfg4 yields ~10 k hits per frame)
+MAX_DET = {"cfg2": 4096, "cfg3": 4096, "cfg4": 32768}
+
+
+def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_input=False):
+    """One chain workload (cfg2 / cfg3 / cfg4) on every rank: K timed steps with D batches in flight (device-resident input,
+    CUDA events, max over ranks; for N > 1 each step ends with the exchange of the detection lists), per-stage times of one
+    lane alone, and the end-to-end figure through the host entry points.  Collective: every rank must call it."""
     torch, pkg, dev, rank, world = env.torch, env.pkg, env.dev, env.rank, env.world
-    w = WORKLOADS[args.workload]
-    S, C, A, F, cfg_idx = w["S"], w["C"], w["A"], args.frames or w["F"], w["idx"]
-    K, W = args.steps, args.warmup
-
-    # `inflight` batches in flight: one context + stream + input batch per lane, steps go round-robin over the lanes, so the
-    # tail of one batch's persistent FFT kernels and its latency-bound detection kernels fill with the next batch's work
-    # (profiles/experiments: 1 -> 2 in flight is +10 % on cfg3).  Lane 0 is the one the per-stage numbers are taken from.
-    D = max(1, args.inflight)
-    gather_records = min(F * 4096, 32768)
+    w = WORKLOADS[name]
+    S, C, A, cfg_idx = w["S"], w["C"], w["A"], w["idx"]
+    max_det = MAX_DET[name]
     side = torch.cuda.Stream(device=dev) if world > 1 else None
+    host_split = [0.0, 0.0]                                # host seconds inside process_device / inside the exchange's run()
+    shared = {}
 
     class Lane:
         def __init__(self, i):
-            self.ctx = pkg.RadarContext(S, C, A, F, keep_doppler_cube=args.keep_cube, max_det_per_frame=4096, device=env.local_rank)
+            self.ctx = pkg.RadarContext(S, C, A, F, keep_doppler_cube=keep_cube, max_det_per_frame=max_det, device=env.local_rank)
             first_frame = (i * world + rank) * F              # weak scaling: every rank owns F frames of each global batch
             self.ctx.set_frame_offset(first_frame)
-            self.adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=cfg_idx + 1, first_frame=first_frame)
+            if share_input and "adc" in shared:
+                self.adc = shared["adc"]                      # side measurements: the lanes read one batch (still larger than L2)
+            else:
+                self.adc = shared["adc"] = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=cfg_idx + 1, first_frame=first_frame)
             self.stream = torch.cuda.Stream(device=dev)
             self.ctx.use_stream(self.stream.cuda_stream)
-            # exchange step (N > 1 only): fixed-size NCCL gather of each rank's result block to rank 0 + one merge kernel, on a
-            # side stream behind a snapshot of the block so that it overlaps the next step's kernels (sharding.DetectionGather)
-            self.gather = pkg.sharding.DetectionGather(self.ctx, dev, gather_records, side=side) if world > 1 else None
+            self.gather = None
 
         def step(self):
             with torch.cuda.stream(self.stream):
@@ -348,21 +358,35 @@ def run_chain(args, env):
                 with torch.cuda.stream(self.stream):
                     self.gather.flush()
 
-    host_split = [0.0, 0.0]                                # host seconds inside process_device / inside the exchange's run()
     lanes = [Lane(i) for i in range(D)]
-    ctx, adc, gather = lanes[0].ctx, lanes[0].adc, lanes[0].gather
+    ctx, adc = lanes[0].ctx, lanes[0].adc
     torch.cuda.synchronize()
     dense_ptr, header_ptr = ctx.device_results()
     header_view = pkg.sharding.device_bytes_view(header_ptr, 16, dev)
+
+    # one batch per lane before anything is sized or timed: the detection counts of this scene size the exchange
+    for ln in lanes:
+        ln.step()
+    torch.cuda.synchronize()
+    hdr0 = header_view.view(torch.int32).cpu().numpy()
+    local_written = int(hdr0[0])
+    # exchange step (N > 1 only): NCCL gather of a fixed-size prefix of each rank's result block to rank 0 + one merge kernel,
+    # on a side stream behind a snapshot of the block so that it overlaps the next step's kernels (sharding.DetectionGather).
+    # The prefix is sized from the warm-up batch (largest count over the ranks + 50 % head-room, whole KB of records):
+    # a rank that outgrows it is truncated and flagged (overflow below), never silently.
+    gather_records = 0
+    if world > 1:
+        most = int(max(env.all_ranks(float(local_written))))
+        gather_records = min(F * max_det, ((most * 3 // 2 + 1024) // 1024) * 1024)
+        for ln in lanes:
+            ln.gather = pkg.sharding.DetectionGather(ln.ctx, dev, gather_records, side=side)
+    gather = lanes[0].gather
 
     for k in range(max(W, D)):
         lanes[k % D].step()
     for ln in lanes:
         ln.flush()
     env.sync_all()
-    sampler = ClockSampler(env.local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(lanes[0].stream)
     for ln in lanes[1:]:
@@ -385,40 +409,37 @@ def run_chain(args, env):
     host_ms_by_rank = env.all_ranks(t_host)
     ms = max(ms_by_rank)
     frame_counts = ctx.read_counts(F)                       # true per-frame hit counts of this rank's last batch
+    hdr = header_view.view(torch.int32).cpu().numpy()
+    local_overflow = int(hdr[3]) or int(frame_counts.max() > max_det)
     if world == 1:
-        n_det_step, gather_overflow = int(header_view[:4].view(torch.int32).item()), 0
+        n_det_step, gather_overflow = int(hdr[0]), 0
     elif rank == 0:
-        recs, hdr = gather.read(pkg.DET_DTYPE)
-        n_det_step, gather_overflow = len(recs), int(hdr[3])
-        assert np.all(np.diff(recs["frame"].astype(np.int64)) >= 0) and int(hdr[2]) == world * F     # ordered, all frames accounted for
+        recs, ghdr = gather.read(pkg.DET_DTYPE)
+        n_det_step, gather_overflow = len(recs), int(ghdr[3])
+        assert np.all(np.diff(recs["frame"].astype(np.int64)) >= 0) and int(ghdr[2]) == world * F     # ordered, all frames accounted for
     else:
         n_det_step, gather_overflow = 0, 0
+    overflow = int(max(env.all_ranks(float(local_overflow or gather_overflow))))
 
     # ---- per-stage device times (events between launches) for the roofline of the dominant kernel ----
     ctx.use_stream(None)
     iters = max(3, min(K, 10))
     total_ms, stage_ms = ctx.time_device(adc, F, iters, per_stage=True)
-    stage_ms = [s / iters for s in stage_ms]
+    stage_ms = [x / iters for x in stage_ms]
     N_adc, N, M = S * C * A, ctx.Sp * ctx.Cp * A, ctx.Sp * ctx.Cp
     stage_bytes = [
         F * (4 * N_adc + 8 * A * ctx.Sp * C),                   # K1: int16 IQ in, range spectrum out
-        F * (8 * A * ctx.Sp * C + (8 * N if args.keep_cube else 0) + 4 * M),   # K2: spectrum in, (cube +) power map out
+        F * (8 * A * ctx.Sp * C + (8 * N if keep_cube else 0) + 4 * M),   # K2: spectrum in, (cube +) power map out
         F * (4 * M + M // 8),                                   # K3: power map in, bit mask out
         F * (M // 8),                                           # K4a+K4b: mask in (+ D records)
     ]
-    names = ["range_fft_kernel", "doppler_fft_kernel", "cfar_kernel", "list_kernel+measure_kernel"]
-    dom = int(np.argmax(stage_ms))
-    peak, peak_src = peaks()
-    achieved = stage_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
-    b_alg = int(ctx.info.algorithmic_bytes_per_frame)
-    fps = world * F * K / (ms * 1e-3)
 
     # ---- end to end through the host-facing API: pinned host capture -> H2D -> chain -> D2H list ----
     host = torch.empty((F, ctx.frame_shorts), dtype=torch.int16, pin_memory=True)
     host.copy_(adc)
     torch.cuda.synchronize()
     out = np.empty(F * ctx.max_det_per_frame, pkg.DET_DTYPE)
-    e2e_steps = max(3, min(K, 10))
+    e2e_steps = e2e_steps or max(3, min(K, 10))
     # two batches in flight (mmw_submit_host / mmw_wait on two contexts) keep the bus busy while the previous batch's last
     # kernels and read-back finish; with one lane only: the synchronous call
     e2e_ring = [ln.ctx for ln in lanes[:2]]
@@ -444,57 +465,123 @@ def run_chain(args, env):
     t0 = time.perf_counter()
     dets = e2e_pass(e2e_steps)
     t_e2e = env.max_over_ranks(time.perf_counter() - t0)
-    e2e_fps = world * F * e2e_steps / t_e2e
-    clocks = sampler.stop() if rank == 0 else None      # sampled every 200 ms from the timed region to the end of the e2e loop
+    res = dict(
+        name=name, F=F, K=K, W=W, D=D, keep_cube=keep_cube, S=S, C=C, A=A, Sp=ctx.Sp, Cp=ctx.Cp,
+        fps=world * F * K / (ms * 1e-3), ms=ms, ms_by_rank=ms_by_rank, host_ms_by_rank=host_ms_by_rank,
+        host_split=list(host_split), total_ms_one=total_ms / iters, stage_ms=stage_ms, stage_bytes=stage_bytes,
+        b_alg=int(ctx.info.algorithmic_bytes_per_frame), kernels_per_batch=int(ctx.info.kernels_per_batch),
+        n_det_step=n_det_step, max_det_frame=int(frame_counts.max()), max_det=max_det, overflow=overflow,
+        gather_records=gather_records, gather_overflow=gather_overflow,
+        e2e_fps=world * F * e2e_steps / t_e2e, e2e_steps=e2e_steps, e2e_dets=len(dets), e2e_two=len(e2e_ring) > 1,
+        h2d_bytes=F * 4 * N_adc, N_adc=N_adc,
+    )
+    for ln in lanes:
+        ln.ctx.close()
+        ln.adc = None
+    shared.clear()
+    del adc, host, lanes
+    torch.cuda.empty_cache()
+    if overflow:
+        raise SystemExit(f"bench.py: {name}: detection list overflow (most hits in one frame {res['max_det_frame']}, capacity {max_det}; "
+                         f"exchange overflow {gather_overflow}): the timed work would be a truncated list — refusing to report it")
+    return res
+
+
+def compact_chain(res, world):
+    """the short form of a chain measurement kept under other_workloads of the default line"""
+    peak = peaks()[0]
+    w = WORKLOADS[res["name"]]
+    F, K, ms = res["F"], res["K"], res["ms"]
+    return {
+        "workload": chain_workload_text(res["name"]), "frames_per_gpu_per_step": F, "steps": K, "batches_in_flight": res["D"],
+        "value": res["fps"], "unit": "frames/s", "ms_per_step": ms / K, "ms_per_step_one_in_flight": res["total_ms_one"],
+        "stage_ms": dict(zip(STAGE_NAMES, res["stage_ms"])),
+        "pipeline_frac_of_measured_hbm_peak": res["b_alg"] * F * K / (ms * 1e-3) / 1e9 / peak,
+        "moved_frac_of_measured_hbm_peak": sum(res["stage_bytes"]) * K / (ms * 1e-3) / 1e9 / peak,
+        "e2e": {"value": res["e2e_fps"], "unit": "frames/s", "h2d_bytes_per_step": res["h2d_bytes"],
+                "d2h_bytes_per_step": 32 + 24 * res["e2e_dets"], "steps": res["e2e_steps"]},
+        "detections_per_step": res["n_det_step"], "max_detections_in_one_frame": res["max_det_frame"],
+        "max_det_per_frame": res["max_det"], "overflow": res["overflow"],
+        "exchange_records_per_rank": res["gather_records"] if world > 1 else None,
+        "config_index": w["idx"],
+    }
+
+
+def run_chain(args, env):
+    """cfg2 / cfg3 / cfg4: batches through the whole chain"""
+    pkg, rank, world = env.pkg, env.rank, env.world
+    w = WORKLOADS[args.workload]
+    S, C, A, F, cfg_idx = w["S"], w["C"], w["A"], args.frames or w["F"], w["idx"]
+    K, W = args.steps, args.warmup
+    # `inflight` batches in flight: one context + stream + input batch per lane, steps go round-robin over the lanes, so the
+    # tail of one batch's persistent FFT kernels and its latency-bound detection kernels fill with the next batch's work
+    # (profiles/experiments: 1 -> 2 in flight is +10 % on cfg3).  Lane 0 is the one the per-stage numbers are taken from.
+    D = max(1, args.inflight)
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    res = measure_chain(env, args.workload, F, K, W, D, keep_cube=args.keep_cube)
+    # the other BASELINE.json configs beside the headline shape, on the same box and the same N: configs[1] (cfg2),
+    # configs[3] (cfg4, frame-sharded) and configs[4] (cfg5, sensors sharded) — shorter runs, same method
+    others = {}
+    if args.workload == "cfg3" and not args.no_other:
+        for name in ("cfg2", "cfg4"):
+            r = measure_chain(env, name, WORKLOADS[name]["F"], 6, 3, 2, share_input=True)
+            others[name] = compact_chain(r, world)
+        others["cfg5"] = compact_stream(measure_stream(env, "cfg5", WORKLOADS["cfg5"]["F"], 3, 3, depth=4, graph=True), world)
+    clocks = sampler.stop() if rank == 0 else None      # sampled every 200 ms from the first timed region to the end of the last
 
     if rank == 0:
-        traffic = NCU_TRAFFIC_BYTES.get(args.workload) if (names[dom] == "range_fft_kernel" and F == w["F"] and not args.keep_cube) else None
+        stage_ms, stage_bytes, ms = res["stage_ms"], res["stage_bytes"], res["ms"]
+        dom = int(np.argmax(stage_ms))
+        peak, peak_src = peaks()
+        achieved = stage_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        b_alg = res["b_alg"]
+        traffic, traffic_src = (None, None)
+        if F == w["F"] and not args.keep_cube:
+            traffic, traffic_src = ncu_traffic(args.workload, STAGE_NAMES[dom])
+        gather_bytes = 32 + 24 * res["gather_records"]
         line = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world,
+            "metric": METRIC, "value": res["fps"], "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": chain_workload_text(args.workload),
                 "frames_per_gpu_per_step": F,
                 "batches_in_flight": D,
-                "ms_per_step_one_in_flight": total_ms / iters,
-                "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a fixed {32 + 24 * gather_records}-byte result block per rank to rank 0 + merge kernel on a side stream, overlapping the next step (overflow={gather_overflow})"),
+                "ms_per_step_one_in_flight": res["total_ms_one"],
+                "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a {gather_bytes}-byte result-block prefix per rank (sized from the warm-up batch) to rank 0 + merge kernel on a side stream, overlapping the next step (overflow={res['gather_overflow']})"),
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
-                "l2": f"inputs larger than L2: {F * 4 * N_adc / 1e6:.0f} MB int16 capture + {F * 8 * A * ctx.Sp * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
-                "ms_per_step_by_rank": [m / K for m in ms_by_rank], "host_issue_ms_per_step_by_rank": [m / K for m in host_ms_by_rank],
-                "host_issue_split_ms_per_step_rank0": {"process_device": host_split[0] / K * 1e3, "exchange": host_split[1] / K * 1e3},
+                "l2": f"inputs larger than L2: {F * 4 * res['N_adc'] / 1e6:.0f} MB int16 capture + {F * 8 * A * res['Sp'] * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
+                "ms_per_step_by_rank": [m / K for m in res["ms_by_rank"]], "host_issue_ms_per_step_by_rank": [m / K for m in res["host_ms_by_rank"]],
+                "host_issue_split_ms_per_step_rank0": {"process_device": res["host_split"][0] / K * 1e3, "exchange": res["host_split"][1] / K * 1e3},
                 "rank0_numa_node": env.numa,
-                "detections_per_step": n_det_step, "max_detections_in_one_frame": int(frame_counts.max()),
-                "max_det_per_frame": ctx.max_det_per_frame,
+                "detections_per_step": res["n_det_step"], "max_detections_in_one_frame": res["max_det_frame"],
+                "max_det_per_frame": res["max_det"], "overflow": res["overflow"],
             },
             "roofline": {
-                "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "bound": "hbm", "kernel": STAGE_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "note": "peak is the 1:1 copy figure of MEASURED_PEAKS.json; a bare data mover with this kernel's 1 : 2 read:write mix reaches "
                         "5.75 TB/s with contiguous stores and 5.2 TB/s with 128-byte corner-turned pieces like this kernel's at 512 points "
                         "(profiles/membench_r1.txt)",
                 "algorithmic_bytes_per_launch": stage_bytes[dom], "kernel_ms": stage_ms[dom],
-                "stage_ms": dict(zip(names, stage_ms)),
-                "stage_gbs": {n: (b / (t * 1e-3) / 1e9 if t > 0 else None) for n, b, t in zip(names, stage_bytes, stage_ms)},
+                "stage_ms": dict(zip(STAGE_NAMES, stage_ms)),
+                "stage_gbs": {n: (b / (t * 1e-3) / 1e9 if t > 0 else None) for n, b, t in zip(STAGE_NAMES, stage_bytes, stage_ms)},
                 "pipeline": {"algorithmic_bytes_per_frame": b_alg, "achieved": b_alg * F * K / (ms * 1e-3) / 1e9,
                              "frac": b_alg * F * K / (ms * 1e-3) / 1e9 / peak, "frac_of_8000_nominal": b_alg * F * K / (ms * 1e-3) / 1e9 / 8000.0,
                              "moved_bytes_per_frame": sum(stage_bytes) // F, "moved_frac": sum(stage_bytes) * K / (ms * 1e-3) / 1e9 / peak,
                              "note": "achieved/frac: 28N+8M bytes/frame (SURVEY.md 8d) x frames / step time, per GPU; moved_*: the bytes "
                                      "the kernels of this build actually read and write (fused mode skips the cube)"},
             },
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": F * 4 * N_adc,
-                    "d2h_bytes_per_step": 32 + 24 * len(dets), "steps": e2e_steps,
-                    "api": "mmw_submit_host + mmw_wait, two batches in flight (one context each)" if len(e2e_ring) > 1 else "mmw_process_host"},
-            "gpu_launches": K * (ctx.info.kernels_per_batch + (1 if world > 1 else 0)),
+            "e2e": {"value": res["e2e_fps"], "unit": "frames/s", "h2d_bytes_per_step": res["h2d_bytes"],
+                    "d2h_bytes_per_step": 32 + 24 * res["e2e_dets"], "steps": res["e2e_steps"],
+                    "api": "mmw_submit_host + mmw_wait, two batches in flight (one context each)" if res["e2e_two"] else "mmw_process_host"},
+            "gpu_launches": K * (res["kernels_per_batch"] + (1 if world > 1 else 0)),      # + rank 0's merge kernel (NCCL's own kernel is not counted)
             "clocks": clocks,
         }
-        if args.workload == "cfg3" and world == 1 and not args.no_other:
-            for ln in lanes:
-                ln.ctx.close()
-                ln.adc = None
-            del adc
-            torch.cuda.empty_cache()
-            line["other_workloads"] = {"cfg2": quick_chain(env, "cfg2")}
+        if others:
+            line["other_workloads"] = others
         if not args.no_cpu_baseline and world == 1:
             orc = entry.load_oracle()
             orc.build()
@@ -506,40 +593,43 @@ def run_chain(args, env):
                                     "sample": f"{n} frames ({port.pool.shape[0]} distinct, {passes} passes) of the same workload in {dt:.1f} s; "
                                               f"plain-C fp64 oracle (the reference has no CPU code for these stages), {port.cores} OpenMP threads"}
         env.emit(line)
-    for ln in lanes:
-        ln.ctx.close()
 
 
-def run_stream(args, env):
+def measure_stream(env, name, sensors_total, K, W, depth=4, graph=True):
     """cfg5: 64 sensors x (256 x 128 x 12) at 30 fps — latency mode.  Every frame is its own call (a sensor's frame is
     processed the moment it arrives); sensors are pinned to GPUs (sensor mod N).  A step = one tick = one frame from
-    every sensor of this rank."""
+    every sensor of this rank.  Collective: every rank must call it."""
     torch, pkg, dev, rank, world = env.torch, env.pkg, env.dev, env.rank, env.world
-    w = WORKLOADS[args.workload]
+    w = WORKLOADS[name]
     S, C, A, cfg_idx = w["S"], w["C"], w["A"], w["idx"]
-    sensors_total = args.frames or w["F"]
-    sensors = [s for s in range(sensors_total) if s % world == rank]
+    sensors = [x for x in range(sensors_total) if x % world == rank]
     F = len(sensors)
-    K, W = args.steps, args.warmup
     ctx = pkg.RadarContext(S, C, A, F, max_det_per_frame=4096, device=env.local_rank)
-    ctx.set_graph_mode(not args.no_graph)
-    adc = torch.stack([pkg.synth.cube_batch_torch(1, S, C, A, dev, cfg=cfg_idx + 1, first_frame=s)[0] for s in sensors])
+    ctx.set_graph_mode(graph)
+    adc = torch.stack([pkg.synth.cube_batch_torch(1, S, C, A, dev, cfg=cfg_idx + 1, first_frame=x)[0] for x in sensors])
     host = torch.empty((F, ctx.frame_shorts), dtype=torch.int16, pin_memory=True)
     host.copy_(adc)
     torch.cuda.synchronize()
     out = np.empty(ctx.max_det_per_frame, pkg.DET_DTYPE)
     frames = [host[i] for i in range(F)]
     dframes = [adc[i] for i in range(F)]
+    tick_no = [0]
+
+    def frame_index(i):
+        # a running frame index per call, as a live stream has: graph mode patches it into the one captured graph
+        return tick_no[0] * sensors_total + sensors[i]
 
     def tick_host(lat=None):
         n = 0
         for i in range(F):
             t0 = time.perf_counter()
-            ctx.set_frame_offset(sensors[i])
-            dets, _ = ctx.process_host(frames[i], 1, out=out)
+            ctx.set_frame_offset(frame_index(i))
+            dets, ov = ctx.process_host(frames[i], 1, out=out)
             if lat is not None:
                 lat.append(time.perf_counter() - t0)
             n += len(dets)
+            assert not ov
+        tick_no[0] += 1
         return n
 
     # device-resident: one launch sequence (or graph replay) per frame, back to back, no host sync in between
@@ -548,9 +638,6 @@ def run_stream(args, env):
         for i in range(F):
             ctx.process_device(dframes[i], 1)
     env.sync_all()
-    sampler = ClockSampler(env.local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     st = torch.cuda.ExternalStream(ctx.stream, device=dev)
     e0.record(st)
@@ -560,7 +647,6 @@ def run_stream(args, env):
     e1.record(st)
     env.sync_all()
     ms = env.max_over_ranks(e0.elapsed_time(e1))
-    fps = sensors_total * K / (ms * 1e-3)
 
     # host path: every frame H2D -> chain -> D2H, synchronous per frame; wall-clock latency per call
     for _ in range(W):
@@ -571,14 +657,14 @@ def run_stream(args, env):
     n_det = 0
     for _ in range(K):
         n_det = tick_host(lat)
-    t_e2e = env.max_over_ranks(time.perf_counter() - t0)
+    t_sync = env.max_over_ranks(time.perf_counter() - t0)
     lat_us = np.sort(np.array(lat)) * 1e6
     # the same calls split in two (mmw_submit_host / mmw_wait) over a ring of contexts: `depth` frames in flight, the upload
     # of frame k+1 under the kernels and read-back of frame k
-    depth = max(1, args.depth)
+    depth = max(1, depth)
     ring = [pkg.RadarContext(S, C, A, 1, max_det_per_frame=4096, device=env.local_rank) for _ in range(depth)]
     for c in ring:
-        c.set_graph_mode(not args.no_graph)
+        c.set_graph_mode(graph)
 
     def tick_pipelined():
         n = 0
@@ -587,8 +673,9 @@ def run_stream(args, env):
             if i >= depth:
                 n += len(c.wait(out=out)[0])
             if i < F:
-                c.set_frame_offset(sensors[i])
+                c.set_frame_offset(frame_index(i))
                 c.submit_host(frames[i], 1)
+        tick_no[0] += 1
         return n
 
     for _ in range(W):
@@ -611,34 +698,77 @@ def run_stream(args, env):
     for _ in range(max(3, K)):
         ctx.process_host(host, F, out=big)
     tick_batched_ms = (time.perf_counter() - t1) / max(3, K) * 1e3
+    res = dict(
+        name=name, S=S, C=C, A=A, cfg_idx=cfg_idx, sensors_total=sensors_total, F=F, K=K, W=W, depth=depth, graph=graph,
+        fps=sensors_total * K / (ms * 1e-3), ms=ms, n_theta=ctx.n_theta, b_alg=int(ctx.info.algorithmic_bytes_per_frame),
+        kernels_per_batch=int(ctx.info.kernels_per_batch), frame_shorts=ctx.frame_shorts,
+        lat_p50=float(lat_us[len(lat_us) // 2]), lat_p99=float(lat_us[min(len(lat_us) - 1, int(0.99 * len(lat_us)))]),
+        lat_max=float(lat_us[-1]), lat_n=int(len(lat_us)), tick_batched_ms=tick_batched_ms,
+        sync_fps=sensors_total * K / t_sync, pipe_fps=sensors_total * K / t_pipe, t_pipe=t_pipe, n_det=n_det,
+    )
+    ctx.close()
+    del adc, host
+    torch.cuda.empty_cache()
+    return res
+
+
+def compact_stream(res, world):
+    """the short form of the streaming measurement kept under other_workloads of the default line"""
+    return {
+        "workload": f"cfg5: {res['sensors_total']} sensors x ({res['S']} x {res['C']} x {res['A']}), one call per frame (latency mode) "
+                    f"(BASELINE.json configs[{res['cfg_idx']}])",
+        "sensors_per_gpu": res["F"], "sharding": f"sensor mod {world}", "cuda_graph": res["graph"], "steps": res["K"],
+        "value": res["fps"], "unit": "frames/s", "required_frames_per_s": 30 * res["sensors_total"],
+        "latency_us": {"p50": res["lat_p50"], "p99": res["lat_p99"], "max": res["lat_max"], "samples": res["lat_n"],
+                       "what": "wall clock of one mmw_process_host(1 frame) call: pinned host -> H2D -> kernels -> D2H -> return"},
+        "e2e": {"value": res["pipe_fps"], "unit": "frames/s", "h2d_bytes_per_step": res["F"] * res["frame_shorts"] * 2,
+                "d2h_bytes_per_step": res["F"] * 32 + 24 * res["n_det"], "steps": res["K"],
+                "api": f"mmw_submit_host + mmw_wait, 1 frame per call, {res['depth']} frames in flight (one context each)"},
+        "realtime_margin_x": (1000.0 / 30.0) / (res["t_pipe"] / res["K"] * 1e3),
+        "config_index": res["cfg_idx"],
+    }
+
+
+def run_stream(args, env):
+    """cfg5 as its own bench line"""
+    pkg, rank, world = env.pkg, env.rank, env.world
+    w = WORKLOADS[args.workload]
+    S, C, A, cfg_idx = w["S"], w["C"], w["A"], w["idx"]
+    sensors_total = args.frames or w["F"]
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    res = measure_stream(env, args.workload, sensors_total, K, W, depth=args.depth, graph=not args.no_graph)
     clocks = sampler.stop() if rank == 0 else None
+    F, ms = res["F"], res["ms"]
     if rank == 0:
         peak, peak_src = peaks()
-        b_alg = int(ctx.info.algorithmic_bytes_per_frame)
+        b_alg = res["b_alg"]
         line = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "metric": METRIC, "value": res["fps"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": f"cfg5: {sensors_total} sensors x ({S} x {C} x {A}), one call per frame (latency mode), 2-D CA-CFAR, "
-                            f"{ctx.n_theta}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
+                            f"{res['n_theta']}-pt angle FFT (BASELINE.json configs[{cfg_idx}])",
                 "sensors_per_gpu": F, "sharding": f"sensor mod {world}", "cuda_graph": not args.no_graph,
                 "required_frames_per_s": 30 * sensors_total,
-                "latency_us": {"p50": float(lat_us[len(lat_us) // 2]), "p99": float(lat_us[min(len(lat_us) - 1, int(0.99 * len(lat_us)))]),
-                               "max": float(lat_us[-1]), "samples": int(len(lat_us)),
-                               "what": "wall clock of one mmw_process_host(1 frame) call: pinned host -> H2D -> 5 kernels -> D2H -> return"},
-                "tick_as_one_batch_ms": tick_batched_ms, "realtime_margin_x": (1000.0 / 30.0) / (t_pipe / K * 1e3),
-                "one_call_per_frame_synchronous_frames_per_s": sensors_total * K / t_e2e,
+                "latency_us": {"p50": res["lat_p50"], "p99": res["lat_p99"], "max": res["lat_max"], "samples": res["lat_n"],
+                               "what": "wall clock of one mmw_process_host(1 frame) call: pinned host -> H2D -> kernels -> D2H -> return"},
+                "tick_as_one_batch_ms": res["tick_batched_ms"], "realtime_margin_x": (1000.0 / 30.0) / (res["t_pipe"] / K * 1e3),
+                "one_call_per_frame_synchronous_frames_per_s": res["sync_fps"],
+                "frame_index": "advances with every call (graph mode patches it into the captured graph: no re-capture)",
                 "l2": "latency mode: one 1.5 MB frame per call (fits L2 by construction; this workload is launch/PCIe-latency bound, not HBM bound)",
-                "detections_last_tick": n_det,
+                "detections_last_tick": res["n_det"],
             },
             "roofline": {"bound": "hbm", "kernel": "whole chain (latency-bound)", "achieved": b_alg * sensors_total * K / (ms * 1e-3) / 1e9 / world,
                          "peak": peak, "unit": "GB/s", "frac": b_alg * sensors_total * K / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg,
                          "note": "SURVEY.md 8d: cfg5 is latency-bound; the figure to read is config.latency_us"},
-            "e2e": {"value": sensors_total * K / t_pipe, "unit": "frames/s", "h2d_bytes_per_step": F * ctx.frame_shorts * 2,
-                    "d2h_bytes_per_step": F * 32 + 24 * n_det, "steps": K,
-                    "api": f"mmw_submit_host + mmw_wait, 1 frame per call, {depth} frames in flight (one context each)"},
-            "gpu_launches": K * F * (ctx.info.kernels_per_batch + 1), "clocks": clocks,      # +1: power_sum_kernel of the antenna-split Doppler path
+            "e2e": {"value": res["pipe_fps"], "unit": "frames/s", "h2d_bytes_per_step": F * res["frame_shorts"] * 2,
+                    "d2h_bytes_per_step": F * 32 + 24 * res["n_det"], "steps": K,
+                    "api": f"mmw_submit_host + mmw_wait, 1 frame per call, {res['depth']} frames in flight (one context each)"},
+            "gpu_launches": K * F * (res["kernels_per_batch"] + 1), "clocks": clocks,      # +1: power_sum_kernel of the antenna-split Doppler path
         }
         if not args.no_cpu_baseline and world == 1:
             orc = entry.load_oracle()
@@ -649,7 +779,6 @@ def run_stream(args, env):
             line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": port.cores, "kind": "port",
                                     "sample": f"{n} frames in {dt:.1f} s, plain-C fp64 oracle, {port.cores} OpenMP threads (frame-parallel)"}
         env.emit(line)
-    ctx.close()
 
 
 def run_legacy(args, env):
@@ -693,7 +822,7 @@ def run_legacy(args, env):
     for _ in range(e2e_steps):
         pkg.api.legacy_process_frames(host, base)
     t_e2e = env.max_over_ranks(time.perf_counter() - t0)
-    os.environ["MMW_LEGACY_QUIET"] = "1"
+    pkg.api.legacy_configure(quiet=1)
     timers = np.zeros(4)
     pkg.cudaProcessing(distinct[1], base, timers=timers)
     t0 = time.perf_counter()
@@ -740,7 +869,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames (cfg5: sensors) per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other", action="store_true", help="cfg3: skip the side measurement of cfg2 (configs[1])")
+    ap.add_argument("--no-other", action="store_true", help="cfg3: skip the side measurements of cfg2 / cfg4 / cfg5 (configs[1], [3], [4])")
     ap.add_argument("--inflight", type=int, default=3, help="cfg2/cfg3/cfg4: batches in flight (contexts on their own streams, steps round-robin)")
     ap.add_argument("--depth", type=int, default=4, help="cfg5: one-frame calls in flight on the end-to-end path (ring of contexts, mmw_submit_host / mmw_wait)")
     ap.add_argument("--no-graph", action="store_true", help="cfg5: launch the kernels one by one instead of replaying a CUDA graph")

@@ -42,6 +42,7 @@ C_ABI_SYMBOLS = [
     "mmw_set_graph_mode", "mmw_set_base_frame", "mmw_process_capture_file", "mmw_default_radar_params", "mmw_to_physical",
     "mmw_legacy_process_frame", "mmw_legacy_process_frames", "mmw_legacy_copy_spectrum", "mmw_legacy_shutdown",
     "mmw_legacy_process_device", "mmw_legacy_sync", "mmw_legacy_distance_from_raw", "mmw_legacy_process_file",
+    "mmw_legacy_configure",
 ]
 # the reference's own entry point (acceleration.h:32), C++ linkage
 LEGACY_MANGLED = "_Z14cudaProcessingPsP9Complex_tiPdS2_S2_S2_"
@@ -139,6 +140,7 @@ def load(build_if_missing: bool = True):
     L.mmw_legacy_process_frames.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
     L.mmw_legacy_copy_spectrum.argtypes = [vp]
     L.mmw_legacy_shutdown.restype = None
+    L.mmw_legacy_configure.argtypes = [C.c_int, C.c_int]
     cp = getattr(L, LEGACY_MANGLED)
     cp.restype = C.c_double
     cp.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
@@ -450,6 +452,12 @@ def legacy_process_file(path: str, capacity: int = 4096):
     _check(load().mmw_legacy_process_file(os.fsencode(path), _np_ptr(dist), _np_ptr(raw), capacity, C.byref(n)))
     k = min(n.value, capacity)
     return dist[:k].copy(), raw[:k].copy(), n.value
+
+
+def legacy_configure(kernel_variant: int = -1, quiet: int = -1):
+    """kernel_variant: 0 pick by batch size, 1 one CTA per frame, 2 the 8-CTA cluster kernel; quiet: silence the per-call line.
+    Negative = keep."""
+    _check(load().mmw_legacy_configure(int(kernel_variant), int(quiet)))
 
 
 def legacy_spectrum() -> np.ndarray:

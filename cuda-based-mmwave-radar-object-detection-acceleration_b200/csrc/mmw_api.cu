@@ -84,11 +84,37 @@ struct mmw_ctx {
     size_t workspace_bytes;
     cudaEvent_t ev[6];
     // CUDA-graph mode (mmw_set_graph_mode): the launch sequence of one batch, captured once per distinct
-    // (capture address, frame count, frame offset, base frame, stream) and replayed with one cudaGraphLaunch
+    // (capture address, frame count, base frame, stream) and replayed with one cudaGraphLaunch.  The frame offset is NOT
+    // part of the key: it lives in the kernel parameters of one node (the record writer) and is patched into the
+    // instantiated graph when it changes (cudaGraphExecKernelNodeSetParams: host-side only), so a stream of frames with
+    // advancing indices replays one graph.
     int graph_on;
     int graph_warm;           // the first batch runs eagerly: launchers set function attributes on first use
-    std::map<std::tuple<const void *, int, uint32_t, const void *, void *>, cudaGraphExec_t> *graphs;
+    struct GraphEntry {
+        cudaGraph_t graph;            // kept: the parameter block the patch starts from lives in it
+        cudaGraphExec_t exec;
+        cudaGraphNode_t record_node;  // the kernel node whose PlanDev carries frame_offset (nullptr: none found)
+        cudaKernelNodeParams record_kp;   // its launch parameters as captured (the argument pointers point into `graph`)
+        uint32_t frame_offset;        // value `exec` currently holds
+    };
+    std::map<std::tuple<const void *, int, const void *, void *>, GraphEntry> *graphs;
 };
+
+static void destroy_graphs(mmw_ctx *c)
+{
+    if (!c->graphs) return;
+    for (auto &kv : *c->graphs) {
+        cudaGraphExecDestroy(kv.second.exec);
+        cudaGraphDestroy(kv.second.graph);
+    }
+    c->graphs->clear();
+}
+
+static int env_int(const char *name)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : 0;
+}
 
 #define CK(call)                                                                                          \
     do {                                                                                                  \
@@ -174,7 +200,7 @@ void mmw_destroy(mmw_ctx *c)
     for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->graphs) {
-        for (auto &kv : *c->graphs) cudaGraphExecDestroy(kv.second);
+        destroy_graphs(c);
         delete c->graphs;
     }
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -200,7 +226,8 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
         set_last_error("CFAR window too large for a %dx%d map (limits: guard+train <= 64 range, <= 32 Doppler)", Sp, Cp);
         return MMW_ERR_ARG;
     }
-    if (cfg->max_det_per_frame < 1 || cfg->max_det_per_frame > 8192) { set_last_error("max_det_per_frame must be 1..8192"); return MMW_ERR_ARG; }
+    if (cfg->max_det_per_frame < 1 || cfg->max_det_per_frame > 65536) { set_last_error("max_det_per_frame must be 1..65536"); return MMW_ERR_ARG; }
+    if ((long long)cfg->max_frames * cfg->max_det_per_frame > (1LL << 28)) { set_last_error("max_frames * max_det_per_frame must not exceed 2^28 records"); return MMW_ERR_ARG; }
 
     int dev = cfg->device;
     if (dev < 0) {
@@ -279,8 +306,21 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     p.alpha = cfg->cfar_alpha; p.lambda_over_d = cfg->lambda_over_d;
     p.max_det = cfg->max_det_per_frame; p.keep_cube = cfg->keep_doppler_cube ? 1 : 0; p.frame_offset = 0;
     p.base_adc = nullptr;
+    // kernel-shape overrides of the sweeps under profiles/ and of the kernel-form parity tests: read once, here
+    p.k1_variant = env_int("MMW_K1_VARIANT"); p.k2_variant = env_int("MMW_K2_VARIANT"); p.k3_variant = env_int("MMW_K3_VARIANT");
+    p.k4_variant = env_int("MMW_K4_VARIANT"); p.ctas_per_sm_cap = env_int("MMW_CTAS_PER_SM");
     p.win_r = c->d_win_r; p.win_d = c->d_win_d; p.tw_d = c->d_tw_d; p.tw_a = c->d_tw_a; p.tw1_r = c->d_tw1_r; p.tw1_d = c->d_tw1_d;
 
+    // antenna-split Doppler path of small batches (run_front): per-antenna power maps for the largest batch that still
+    // prefers the split, if that stays modest.  Allocated here, never inside a batch: a batch may be under stream capture.
+    if (A > 1 && !cfg->keep_doppler_cube && doppler_prefers_split(p, 1)) {
+        int cap = 1;
+        while (cap < F && doppler_prefers_split(p, cap + 1)) ++cap;
+        if ((size_t)cap * A * M * sizeof(float) <= ((size_t)128 << 20)) {
+            if ((rc = dev_alloc(c, &c->d_psplit, (size_t)cap * A * M))) return fail(rc);
+            c->psplit_frames = cap;
+        }
+    }
     if ((rc = mmw_set_windows(c, nullptr, nullptr))) return fail(rc);
     *out = c;
     return MMW_OK;
@@ -371,23 +411,7 @@ static int run_front(mmw_ctx *c, const int16_t *adc_dev, int first, int n, cudaE
     if (stage_ev) CK(cudaEventRecord(stage_ev[0], st));
     CK(launch_range_fft(p, adc, rs, n, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[1], st));
-    bool split = !cube && doppler_prefers_split(p, n);
-    if (split && n > c->psplit_frames) {
-        // per-antenna maps for the largest batch that still prefers the split, if that stays modest
-        int cap = n;
-        while (cap < c->cfg.max_frames && doppler_prefers_split(p, cap + 1)) ++cap;
-        const size_t bytes = (size_t)cap * p.A * M * sizeof(float);
-        if (bytes <= ((size_t)128 << 20)) {
-            if (c->d_psplit) { cudaFree(c->d_psplit); c->workspace_bytes -= (size_t)c->psplit_frames * p.A * M * sizeof(float); }
-            c->d_psplit = nullptr;
-            c->psplit_frames = 0;
-            int rc = dev_alloc(c, &c->d_psplit, (size_t)cap * p.A * M);
-            if (rc) return rc;
-            c->psplit_frames = cap;
-        } else {
-            split = false;
-        }
-    }
+    const bool split = !cube && n <= c->psplit_frames && doppler_prefers_split(p, n);     // d_psplit: mmw_create
     if (split) {
         PlanDev q = p;                                   // [F][A][Sp][C] read as F*A single-antenna frames
         q.A = 1;
@@ -431,14 +455,11 @@ static int run_batch_graphed(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
         c->graph_warm = 1;
         return run_batch(c, adc_dev, n_frames, nullptr);
     }
-    if (!c->graphs) c->graphs = new std::map<std::tuple<const void *, int, uint32_t, const void *, void *>, cudaGraphExec_t>();
-    const auto key = std::make_tuple((const void *)adc_dev, n_frames, c->plan.frame_offset, (const void *)c->plan.base_adc, (void *)c->stream);
+    if (!c->graphs) c->graphs = new std::map<std::tuple<const void *, int, const void *, void *>, mmw_ctx::GraphEntry>();
+    const auto key = std::make_tuple((const void *)adc_dev, n_frames, (const void *)c->plan.base_adc, (void *)c->stream);
     auto it = c->graphs->find(key);
     if (it == c->graphs->end()) {
-        if (c->graphs->size() >= 256) {                       // bounded cache: start over rather than track recency
-            for (auto &kv : *c->graphs) cudaGraphExecDestroy(kv.second);
-            c->graphs->clear();
-        }
+        if (c->graphs->size() >= 256) destroy_graphs(c);      // bounded cache: start over rather than track recency
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         const int rc = run_batch(c, adc_dev, n_frames, nullptr);
@@ -450,11 +471,44 @@ static int run_batch_graphed(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
         }
         cudaGraphExec_t exec = nullptr;
         const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ei != cudaSuccess) { set_last_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); return MMW_ERR_CUDA; }
-        it = c->graphs->emplace(key, exec).first;
+        if (ei != cudaSuccess) {
+            cudaGraphDestroy(graph);
+            set_last_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+            return MMW_ERR_CUDA;
+        }
+        mmw_ctx::GraphEntry ge;
+        memset(&ge, 0, sizeof(ge));
+        ge.graph = graph; ge.exec = exec; ge.frame_offset = c->plan.frame_offset;
+        // the node that writes mmw_detection.frame: the only consumer of PlanDev.frame_offset
+        size_t n_nodes = 0;
+        if (cudaGraphGetNodes(graph, nullptr, &n_nodes) == cudaSuccess && n_nodes > 0) {
+            std::vector<cudaGraphNode_t> nodes(n_nodes);
+            if (cudaGraphGetNodes(graph, nodes.data(), &n_nodes) == cudaSuccess)
+                for (size_t i = 0; i < n_nodes; ++i) {
+                    cudaGraphNodeType ty;
+                    cudaKernelNodeParams kp;
+                    if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+                    if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+                    if (is_record_kernel(kp.func)) { ge.record_node = nodes[i]; ge.record_kp = kp; }
+                }
+        }
+        cudaGetLastError();
+        it = c->graphs->emplace(key, ge).first;
     }
-    CK(cudaGraphLaunch(it->second, c->stream));
+    mmw_ctx::GraphEntry &ge = it->second;
+    if (ge.frame_offset != c->plan.frame_offset) {
+        if (!ge.record_node) { set_last_error("graph mode: record-writer node not found, cannot change the frame offset"); return MMW_ERR_STATE; }
+        cudaKernelNodeParams kp = ge.record_kp;
+        PlanDev patched = *reinterpret_cast<const PlanDev *>(kp.kernelParams[0]);       // argument 0 of both record kernels
+        patched.frame_offset = c->plan.frame_offset;
+        void *args[kRecordKernelArgs];
+        for (int i = 0; i < kRecordKernelArgs; ++i) args[i] = kp.kernelParams[i];
+        args[0] = &patched;
+        kp.kernelParams = args;
+        CK(cudaGraphExecKernelNodeSetParams(ge.exec, ge.record_node, &kp));
+        ge.frame_offset = c->plan.frame_offset;
+    }
+    CK(cudaGraphLaunch(ge.exec, c->stream));
     c->last_frames = n_frames;
     return MMW_OK;
 }
@@ -473,21 +527,27 @@ static int check_batch_args(mmw_ctx *c, const void *adc, int n_frames, const cha
     return MMW_OK;
 }
 
+// a misaligned or host pointer would fault inside the TMA copies of the first kernel and leave a sticky context error:
+// refuse it up front
+static int check_device_capture(const void *adc_dev, const char *who)
+{
+    if (((uintptr_t)adc_dev & 15u) != 0) { set_last_error("%s: adc_dev must be 16-byte aligned", who); return MMW_ERR_ARG; }
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, adc_dev);
+    if (e != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        set_last_error("%s: adc_dev is not a device pointer (use mmw_process_host for host captures)", who);
+        return MMW_ERR_ARG;
+    }
+    return MMW_OK;
+}
+
 int mmw_process_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
 {
     int rc = check_batch_args(c, adc_dev, n_frames, "mmw_process_device");
     if (rc) return rc;
-    if (((uintptr_t)adc_dev & 15u) != 0) { set_last_error("mmw_process_device: adc_dev must be 16-byte aligned"); return MMW_ERR_ARG; }
     CK(cudaSetDevice(c->device));
-    {   // a host pointer here would fault inside the first kernel: refuse it up front
-        cudaPointerAttributes at;
-        const cudaError_t e = cudaPointerGetAttributes(&at, adc_dev);
-        if (e != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
-            cudaGetLastError();
-            set_last_error("mmw_process_device: adc_dev is not a device pointer (use mmw_process_host for host captures)");
-            return MMW_ERR_ARG;
-        }
-    }
+    if ((rc = check_device_capture(adc_dev, "mmw_process_device"))) return rc;
     return run_batch_graphed(c, adc_dev, n_frames);
 }
 
@@ -838,6 +898,7 @@ int mmw_time_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames, int iters,
     if (rc) return rc;
     if (iters < 1 || !total_ms) { set_last_error("mmw_time_device: bad iters / null output"); return MMW_ERR_ARG; }
     CK(cudaSetDevice(c->device));
+    if ((rc = check_device_capture(adc_dev, "mmw_time_device"))) return rc;
     cudaStream_t st = c->stream;
     if (per_stage_ms) {
         // separate instrumented pass: events between launches serialise the stages

@@ -27,7 +27,9 @@ struct PlanDev {
     const float2 *tw1_d;    // [Cp]  pass-1 twiddles of the Doppler FFT in consumption order
     const float2 *tw_a;     // [n_theta]
     const int16_t *base_adc; // one frame [C][A][S] IIQQ subtracted before the range window, or nullptr (static-clutter removal)
-    int k2_last_frame_first; // K2 walks the batch from its last frame to its first: the range spectrum K1 wrote last is still in L2
+    // host-side only: kernel-shape overrides for the sweeps under profiles/ and the kernel-form parity tests.  Read ONCE, in
+    // mmw_create (MMW_K1_VARIANT / MMW_K2_VARIANT / MMW_K3_VARIANT / MMW_K4_VARIANT / MMW_CTAS_PER_SM); 0 = pick by shape.
+    int k1_variant, k2_variant, k3_variant, k4_variant, ctas_per_sm_cap;
 };
 
 // internal HBM layouts
@@ -84,12 +86,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-// hint: bring `bytes` (multiple of 16) at `src` (16-byte aligned) into L2; no shared memory, no completion to wait for
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
 __device__ __forceinline__ void st_global_f2(float2 *p, float2 v)
 {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
@@ -119,6 +115,10 @@ struct DetectBuffers {
 };
 cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, int sm_count, cudaStream_t st);
 cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st);
+// the kernels that write mmw_detection records (the only readers of PlanDev.frame_offset, their argument 0): graph mode patches
+// that argument in place instead of re-capturing when the frame offset changes (mmw_api.cu)
+constexpr int kRecordKernelArgs = 12;
+bool is_record_kernel(const void *func);
 cudaError_t launch_merge(const unsigned char *gathered, int n_ranks, size_t stride_bytes, unsigned char *merged, int merged_cap,
                          cudaStream_t st);
 // export helpers (not on the hot path): internal layout -> the canonical layouts of mmw_radar.h

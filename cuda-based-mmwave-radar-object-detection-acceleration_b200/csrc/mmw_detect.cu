@@ -978,18 +978,13 @@ static int cfar_smem_bytes(const PlanDev &p)
     return (th_ * tw_ + 2 * th_ * kCfarRS) * 4 + kCfarRT * 4;
 }
 
-// MMW_K3_VARIANT (profiles/sweep_variants.py): 0 = pick by shape, 1 = always the tiled kernel, 2/3 = walk kernel forced to
-// 64- / 128-bin strips, +10 * nchunk to force the Doppler segment length
-static int cfar_variant()
-{
-    const char *e = getenv("MMW_K3_VARIANT");
-    return e ? atoi(e) : 0;
-}
+// PlanDev.k3_variant (MMW_K3_VARIANT at mmw_create; profiles/sweep_variants.py, tests): 0 = pick by shape, 1 = always the tiled
+// kernel, 2/3/4 = walk kernel forced to 64- / 128- / 256-bin strips, +10 * nchunk to force the Doppler segment length
 
 cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, int sm_count, cudaStream_t st)
 {
     const bool fixed = p.guard_r == 2 && p.guard_d == 2 && p.win_r_half == 10 && p.win_d_half == 6;
-    const int var = cfar_variant();
+    const int var = p.k3_variant;
     if (fixed && p.Sp % 64 == 0 && p.Cp % 32 == 0 && var != 1) {
         // walk form.  Longer Doppler segments amortise the 12-row run-in (28 input rows for the first 16 outputs, 16
         // after that), wider strips the 24-column halo; both are traded against having enough CTAs for every SM.
@@ -1025,6 +1020,11 @@ cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, flo
     else
         cfar_kernel<false><<<grid, kCfarNT, bytes, st>>>(p, pmap, mask, noise_map);
     return cudaGetLastError();
+}
+
+bool is_record_kernel(const void *func)
+{
+    return func == (const void *)measure_kernel || func == (const void *)measure_wide_kernel;
 }
 
 cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st)

@@ -15,7 +15,9 @@
 // returned distance is the reference's even when two bins are within fp32 rounding of each other,
 // every bin within 1e-4 (relative, power) of the fp32 maximum is re-evaluated in fp64 with a direct
 // DFT and the reference's rule (strict >, ascending bin => first maximum wins, cudaBenchMarking.cpp:
-// 191-206) is applied to the fp64 values.
+// 191-206) is applied to the fp64 values.  The near-tie bins are kept as a bit map of the search range,
+// so there is no cap on their number and they are visited in ascending order by construction (a flat
+// spectrum re-evaluates every bin: slow — ~20 us per bin — but never a different answer).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -44,7 +46,7 @@ constexpr int kN = 16384;                          // nextPow2(12 800), accelera
 constexpr int kSearch = 6553;                      // floor(0.4 * 16384), acceleration.cu:522
 constexpr int kFrameShorts = kS * kC * kA * 2;     // 102 400
 constexpr int kNT = 512;
-constexpr int kMaxCand = 32;
+constexpr int kCandWords = (kSearch + 31) / 32;   // near-tie bins as a bit map of the search range [0, kSearch)
 constexpr int kRowShorts = 2 * kS;                 // rx0's I/Q of one chirp: the only part of a frame this chain reads
 constexpr int kFullRowShorts = kA * 2 * kS;        // one chirp of all receivers in the capture
 constexpr int kPackedFrameShorts = kC * kRowShorts;   // 25 600: what the host path uploads per frame (a quarter of the capture)
@@ -69,7 +71,8 @@ __device__ __forceinline__ void load_sample(const LegacyArgs &a, const int16_t *
     const int c = n / kS, s = n - c * kS;
     const int in_row = 4 * (s >> 1) + (s & 1);
     double i16 = 0, q16 = 0;
-    if (c * (kA * 2 * kS) + in_row + 2 < a.size) {
+    // whole IIQQ groups only: the reference unpacks size / 4 groups (acceleration.cu:94-97), an incomplete last group is not read
+    if (c * (kA * 2 * kS) + 4 * (s >> 1) + 4 <= a.size) {
         i16 = (double)frame[c * a.row_stride + in_row];
         q16 = (double)frame[c * a.row_stride + in_row + 2];
     }
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kNT, 1) legacy_frame_kernel(LegacyArgs a)
     float2 *sm = reinterpret_cast<float2 *>(smem_raw);                     // [kN + kN/32]
     __shared__ unsigned long long red_key[kNT / 32];
     __shared__ double red_d[2][kNT / 32];
-    __shared__ int cand[kMaxCand];
+    __shared__ uint32_t cand_bits[kCandWords];
     __shared__ int n_cand;
     __shared__ unsigned long long best_key_s;
 
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(kNT, 1) legacy_frame_kernel(LegacyArgs a)
         sm[phys(n)] = v;
     }
     if (tid == 0) n_cand = 0;
+    if (tid < kCandWords) cand_bits[tid] = 0u;
     __syncthreads();
 
     // ---- pass 1: 1024 radix-16 butterflies, stride 1024 ----
@@ -185,27 +189,18 @@ __global__ void __launch_bounds__(kNT, 1) legacy_frame_kernel(LegacyArgs a)
         for (int q3 = 0; q3 < 13; ++q3) {
             const int k = q1 + 16 * q2 + 512 * q3;
             if (k < kSearch && best_m > 0.f && mag[q3] >= thr) {
-                const int slot = atomicAdd(&n_cand, 1);
-                if (slot < kMaxCand) cand[slot] = k;
+                atomicAdd(&n_cand, 1);
+                atomicOr(&cand_bits[k >> 5], 1u << (k & 31));
             }
         }
     }
     __syncthreads();
-    const int nc = n_cand;
-    if (nc > 1 && nc <= kMaxCand) {
-        if (tid == 0) {                                   // ascending bin order
-            for (int i = 1; i < nc; ++i) {
-                const int v = cand[i];
-                int j = i - 1;
-                while (j >= 0 && cand[j] > v) { cand[j + 1] = cand[j]; --j; }
-                cand[j + 1] = v;
-            }
-        }
-        __syncthreads();
+    if (n_cand > 1) {
         double best64 = 0.0;
         int best64_k = 0;
-        for (int ci = 0; ci < nc; ++ci) {
-            const int k = cand[ci];
+        for (int wi = 0; wi < kCandWords; ++wi)           // ascending bin order; block-uniform control flow
+        for (uint32_t bits = cand_bits[wi]; bits; bits &= bits - 1) {
+            const int k = 32 * wi + __ffs(bits) - 1;
             double sr = 0.0, si = 0.0;
             for (int n = tid; n < kValid; n += kNT) {
                 double xr, xi, s, c;
@@ -281,9 +276,9 @@ __device__ __forceinline__ void dsmem_st_u64(uint32_t addr, unsigned long long v
 {
     asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
-__device__ __forceinline__ void dsmem_st_u32(uint32_t addr, uint32_t v)
+__device__ __forceinline__ void dsmem_atom_or(uint32_t addr, uint32_t v)
 {
-    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    asm volatile("red.shared::cluster.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t dsmem_atom_inc(uint32_t addr)
 {
@@ -299,7 +294,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kNTc, 1) legacy_cl
     __shared__ unsigned long long red_key[kNTc / 32];
     __shared__ unsigned long long cta_keys[kCl];               // CTA 0's copy collects the eight maxima
     __shared__ double red_d[2][kNTc / 32];
-    __shared__ int cand[kMaxCand];
+    __shared__ uint32_t cand_bits[kCandWords];
     __shared__ int n_cand;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -320,6 +315,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kNTc, 1) legacy_cl
         sm[phys16(m)] = v;
     }
     if (tid == 0) n_cand = 0;
+    if (tid < kCandWords) cand_bits[tid] = 0u;
     __syncthreads();
 
     // ---- pass 1: 256 radix-8 butterflies, stride 256 ----
@@ -424,29 +420,20 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kNTc, 1) legacy_cl
         for (int k1 = 0; k1 < 4; ++k1) {
             const int k = 256 * (int)q + tid + kN2 * k1;
             if (k < kSearch && best_m > 0.f && mag[k1] >= thr) {
-                const uint32_t slot = dsmem_atom_inc(dsmem_addr(&n_cand, 0));
-                if (slot < (uint32_t)kMaxCand) dsmem_st_u32(dsmem_addr(&cand[slot], 0), (uint32_t)k);
+                dsmem_atom_inc(dsmem_addr(&n_cand, 0));
+                dsmem_atom_or(dsmem_addr(&cand_bits[k >> 5], 0), 1u << (k & 31));
             }
         }
     }
     cluster_sync_all();
     if (q != 0) return;                                        // nothing reads the other CTAs' shared memory any more
 
-    const int nc = n_cand;
-    if (nc > 1 && nc <= kMaxCand) {
-        if (tid == 0) {                                   // ascending bin order
-            for (int i = 1; i < nc; ++i) {
-                const int v = cand[i];
-                int j = i - 1;
-                while (j >= 0 && cand[j] > v) { cand[j + 1] = cand[j]; --j; }
-                cand[j + 1] = v;
-            }
-        }
-        __syncthreads();
+    if (n_cand > 1) {
         double best64 = 0.0;
         int best64_k = 0;
-        for (int ci = 0; ci < nc; ++ci) {
-            const int k = cand[ci];
+        for (int wi = 0; wi < kCandWords; ++wi)           // ascending bin order; block-uniform control flow
+        for (uint32_t bits = cand_bits[wi]; bits; bits &= bits - 1) {
+            const int k = 32 * wi + __ffs(bits) - 1;
             double sr = 0.0, si = 0.0;
             for (int n = tid; n < kValid; n += kNTc) {
                 double xr, xi, sn, cs;
@@ -495,9 +482,13 @@ struct LegacyState {
     double *h_base_copy = nullptr; // last base frame uploaded
     bool base_valid = false;
     bool quiet = false;
+    int device = 0;                // the device the state lives on: the one that was current at first use
+    int variant = 0;               // 0: kernel picked by batch size, 1: always one CTA per frame, 2: always the 8-CTA cluster
 };
 LegacyState g;
-std::mutex g_mu;
+std::mutex g_mu;                   // every entry point below (shutdown included) holds it
+bool g_atexit_registered = false;
+bool g_env_read = false;
 
 constexpr int kSmemBytes = (kN + kN / 32) * 8;
 
@@ -525,11 +516,24 @@ cudaError_t ensure_frames(int n)
     return cudaSuccess;
 }
 
+void shutdown_locked();
+
+// Called with g_mu held, first thing in every entry point: binds the state to the device that is current at first use and
+// makes that device current on every later call (the caller's thread may have another one current by then).
 cudaError_t ensure_init()
 {
-    if (g.ready) return cudaSuccess;
-    const char *q = getenv("MMW_LEGACY_QUIET");
-    g.quiet = q && q[0] && q[0] != '0';
+    if (g.ready) {
+        LCHECK(cudaSetDevice(g.device));
+        return cudaSuccess;
+    }
+    if (!g_env_read) {               // the environment is read once per process; mmw_legacy_configure overrides it
+        const char *q = getenv("MMW_LEGACY_QUIET");
+        g.quiet = q && q[0] && q[0] != '0';
+        const char *v = getenv("MMW_LEGACY_VARIANT");
+        g.variant = v ? atoi(v) : 0;
+        g_env_read = true;
+    }
+    LCHECK(cudaGetDevice(&g.device));
     LCHECK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     LCHECK(cudaMalloc(&g.d_base, kValid * sizeof(double2)));
     LCHECK(cudaMalloc(&g.d_tw, kN * sizeof(float2)));
@@ -546,7 +550,10 @@ cudaError_t ensure_init()
     LCHECK(cudaFuncSetAttribute(legacy_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     LCHECK(ensure_frames(1));
     g.ready = true;
-    atexit(mmw_legacy_shutdown);
+    if (!g_atexit_registered) {
+        atexit(mmw_legacy_shutdown);
+        g_atexit_registered = true;
+    }
     return cudaSuccess;
 }
 
@@ -572,11 +579,11 @@ double distance_from_raw(int raw)
 // A few frames per launch (the drop-in's one frame per call) are latency-bound: the 8-CTA cluster finishes a frame in about a
 // quarter of the single-CTA kernel's time.  Many frames per launch are throughput-bound, and there one CTA per frame wins
 // (5.0 M against 2.2 M frames/s device-resident: no cluster barriers, no idle half of the CTA in passes 2 and 3); the two
-// lines cross near 60 frames per launch.  MMW_LEGACY_VARIANT = 1 / 2 forces the single-CTA / cluster kernel (profiles/, tests).
+// lines cross near 60 frames per launch.  mmw_legacy_configure (or MMW_LEGACY_VARIANT at first use) = 1 / 2 forces the
+// single-CTA / cluster kernel (profiles/, tests).
 cudaError_t launch_frames(const LegacyArgs &a, int n)
 {
-    const char *v = getenv("MMW_LEGACY_VARIANT");
-    const int var = v ? atoi(v) : 0;
+    const int var = g.variant;
     const bool cluster = var == 2 || (var != 1 && n <= 48);
     if (cluster)
         legacy_cluster_kernel<<<n * kCl, kNTc, 0, g.stream>>>(a);
@@ -639,6 +646,22 @@ cudaError_t run_frames(const short *frames, int n, const double *base, int size,
     LCHECK(launch_frames(a, n));
     LCHECK(cudaStreamSynchronize(g.stream));             // a.raw is mapped host memory (ensure_frames): the results are in g.h_raw
     return cudaSuccess;
+}
+
+void shutdown_locked()
+{
+    if (!g.ready) return;
+    const bool quiet = g.quiet;
+    const int variant = g.variant;
+    // at process exit the context may already be gone; ignore errors
+    cudaSetDevice(g.device);
+    cudaFree(g.d_frames); cudaFree(g.d_base); cudaFree(g.d_tw); cudaFree(g.d_spec);
+    cudaFreeHost(g.h_raw); cudaFreeHost(g.h_stage);
+    if (g.stream) cudaStreamDestroy(g.stream);
+    free(g.h_base_copy);
+    g = LegacyState();
+    g.quiet = quiet;                 // configuration survives a shutdown / re-init cycle
+    g.variant = variant;
 }
 
 double now_s()
@@ -735,6 +758,7 @@ int mmw_legacy_sync(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.ready) return MMW_OK;
+    cudaSetDevice(g.device);
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) {
         mmw::set_last_error("mmw_legacy_sync: %s", cudaGetErrorString(cudaGetLastError()));
         return MMW_ERR_CUDA;
@@ -768,9 +792,10 @@ int mmw_legacy_process_file(const char *path, double *distances, int *raw_indice
         for (int n = 0; n < kValid; ++n) {
             const int c = n / kS, sidx = n - c * kS;
             const int e = c * (kA * kS) + sidx;
-            const size_t gidx = (size_t)4 * (e >> 1) + (e & 1);
-            base[2 * n] = gidx + 2 < got ? (double)buf[gidx] : 0.0;
-            base[2 * n + 1] = gidx + 2 < got ? (double)buf[gidx + 2] : 0.0;
+            const size_t grp = (size_t)4 * (e >> 1), gidx = grp + (e & 1);
+            const bool whole = grp + 4 <= got;                   // whole IIQQ groups only, as in load_sample
+            base[2 * n] = whole ? (double)buf[gidx] : 0.0;
+            base[2 * n + 1] = whole ? (double)buf[gidx + 2] : 0.0;
         }
         std::lock_guard<std::mutex> lk(g_mu);
         while (rc == MMW_OK && (got = fread(buf, sizeof(short), (size_t)kBatch * kFrameShorts, fp)) > 0) {
@@ -805,20 +830,25 @@ int mmw_legacy_copy_spectrum(float *out)
         mmw::set_last_error("mmw_legacy_copy_spectrum: no frame processed yet");
         return MMW_ERR_STATE;
     }
+    cudaSetDevice(g.device);
     if (cudaMemcpy(out, g.d_spec, kN * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) return MMW_ERR_CUDA;
     return MMW_OK;
 }
 
 void mmw_legacy_shutdown(void)
 {
-    if (!g.ready) return;
-    g.ready = false;
-    // at process exit the context may already be gone; ignore errors
-    cudaFree(g.d_frames); cudaFree(g.d_base); cudaFree(g.d_tw); cudaFree(g.d_spec);
-    cudaFreeHost(g.h_raw); cudaFreeHost(g.h_stage);
-    if (g.stream) cudaStreamDestroy(g.stream);
-    free(g.h_base_copy);
-    g = LegacyState();
+    std::lock_guard<std::mutex> lk(g_mu);
+    shutdown_locked();
+}
+
+int mmw_legacy_configure(int kernel_variant, int quiet)
+{
+    if (kernel_variant > 2) { mmw::set_last_error("mmw_legacy_configure: kernel_variant must be 0, 1, 2 or negative (keep)"); return MMW_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_env_read = true;               // explicit configuration wins over the environment from here on
+    if (kernel_variant >= 0) g.variant = kernel_variant;
+    if (quiet >= 0) g.quiet = quiet != 0;
+    return MMW_OK;
 }
 
 }  // extern "C"

@@ -65,7 +65,7 @@ struct RangeSmem {
 // few MB read by every CTA); reading them with per-lane global loads instead costs 4x sector over-fetch and +70 % time.
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE>
 __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1) range_fft_kernel(PlanDev p, const int16_t *__restrict__ adc, float2 *__restrict__ rs,
-                                                            int n_tiles, int l2_ahead)
+                                                            int n_tiles)
 {
     static_assert(R1 * R2 == N, "plan");
     using L = RangeSmem<N, BT, NSTAGE, BASE>;
@@ -109,17 +109,6 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
         }
     };
 
-    // The staging copy of a tile is issued one tile ahead and has only the second FFT pass to land (ncu: a third of the warp
-    // samples sit on the mbarrier wait).  Its rows are therefore pulled into L2 `l2_ahead` tiles earlier with a bulk prefetch
-    // hint (no shared memory, nothing to wait for), so that the staging copy itself is an L2 hit.
-    auto prefetch = [&](int tile) {         // one warp
-        const int ct = tile % nct, fa = tile / nct;
-        const int a = fa % A, f = fa / A;
-        const int c0 = ct * BT;
-        if (lane < min(BT, C - c0))
-            bulk_prefetch_l2(adc + (((size_t)f * C + c0 + lane) * A + a) * (size_t)(2 * S), (uint32_t)(S * 4));
-    };
-
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -128,9 +117,6 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
     __syncthreads();
     int tile = blockIdx.x;
     if (warp == 0 && tile < n_tiles) issue(tile, 0);
-    if (warp == 1 && l2_ahead > 0)
-        for (int j = 1; j <= l2_ahead; ++j)
-            if (tile + j * (int)gridDim.x < n_tiles) prefetch(tile + j * (int)gridDim.x);
     for (int i = tid; i < N; i += NT) tw[i] = p.tw1_r[i];
     for (int i = tid; i < N; i += NT) win[i] = i < S ? p.win_r[i] : 0.f;
     __syncthreads();
@@ -227,9 +213,9 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
         __syncthreads();
         // single staging buffer: it is consumed now, prefetch the next tile behind pass 2.  (Refilling it earlier — as
         // soon as the last warp has pulled its pass-1 inputs into registers — removes the wait on the copy but not a
-        // microsecond of run time: the stall moves to the barrier, profiles/experiments/r1_k1_early_release.md.)
+        // microsecond of run time: the stall moves to the barrier, profiles/experiments/r1_k1_early_release.md.  L2 prefetch
+        // hints for the tiles after that made it slower, r1_k1_l2_prefetch.log.)
         if (NSTAGE == 1 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
-        if (warp == 1 && l2_ahead > 0 && tile + (l2_ahead + 1) * (int)gridDim.x < n_tiles) prefetch(tile + (l2_ahead + 1) * (int)gridDim.x);
 
         // ---- pass 2: R1 butterflies of radix R2 on contiguous runs; outputs go straight to HBM ----
         float2 *out = rs + (size_t)fa * (size_t)N * C + c0 + row;
@@ -327,7 +313,7 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
         const long long tl = (long long)blockIdx.x + (long long)itq * gridDim.x;
         if (tl >= n_tiles) return;
         const int tile = (int)tl;
-        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
+        const int rt = tile % nrt, f = tile / nrt;
         const int buf = q % NSTAGE;
         uint64_t *b = &bar[buf];
         if (lane == 0) {
@@ -368,7 +354,7 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
 
 #pragma unroll 1
     for (; tile < n_tiles; tile += gridDim.x) {
-        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
+        const int rt = tile % nrt, f = tile / nrt;
         const int r0 = rt * BT;
         float acc[UPS2][R2];
 #pragma unroll
@@ -497,7 +483,7 @@ __global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p,
         const long long tl = gw + (long long)itq * nwarp;
         if (tl >= n_tiles) return;
         const int tile = (int)tl;
-        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
+        const int rt = tile % nrt, f = tile / nrt;
         uint64_t *b = &bar[q % NSTAGE];
         if (lane == 0) {
             fence_proxy_async();
@@ -532,7 +518,7 @@ __global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p,
 #pragma unroll 1
     for (long long tl = gw; tl < n_tiles; tl += nwarp) {
         const int tile = (int)tl;
-        const int rt = tile % nrt, f = p.k2_last_frame_first ? n_tiles / nrt - 1 - tile / nrt : tile / nrt;
+        const int rt = tile % nrt, f = tile / nrt;
         float acc[U2][R2];
 #pragma unroll
         for (int u = 0; u < U2; ++u)
@@ -692,17 +678,13 @@ static cudaError_t resident_ctas(K kernel, int threads, int smem_bytes, int *cta
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, threads, smem_bytes);
 }
 
-// MMW_CTAS_PER_SM (experiment): cap of resident CTAs per SM for the persistent FFT kernels, so that the FFT kernels of two
-// batches in flight can share every SM instead of taking turns (profiles/experiments/r1_fft_corun.log)
-static int capped_per_sm(int per_sm)
+// PlanDev.ctas_per_sm_cap (MMW_CTAS_PER_SM at mmw_create; experiment): cap of resident CTAs per SM for the persistent FFT
+// kernels, so that the FFT kernels of two batches in flight can share every SM instead of taking turns
+// (profiles/experiments/r1_fft_corun.log)
+static int capped_per_sm(const PlanDev &p, int per_sm)
 {
-    const char *e = getenv("MMW_CTAS_PER_SM");
-    const int cap = e ? atoi(e) : 0;
-    return cap > 0 && cap < per_sm ? cap : per_sm;
+    return p.ctas_per_sm_cap > 0 && p.ctas_per_sm_cap < per_sm ? p.ctas_per_sm_cap : per_sm;
 }
-
-constexpr int kRangeL2Ahead = 0;
-constexpr int kK2LastFrameFirst = 0;   // default order of K2 over the frames of a batch       // default look-ahead of K1's L2 prefetch hints (tiles)
 
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE = false>
 static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
@@ -718,9 +700,8 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
     }
     const int nct = (p.C + BT - 1) / BT;
     const long long tiles = (long long)n_frames * p.A * nct;
-    const int grid = (int)(tiles < (long long)capped_per_sm(per_sm) * sm_count() ? tiles : (long long)capped_per_sm(per_sm) * sm_count());
-    const char *la = getenv("MMW_K1_L2_AHEAD");                        // tiles of L2 look-ahead (0 = off; profiles/sweep_variants.py)
-    k<<<grid, NW * 32, bytes, st>>>(p, adc, rs, (int)tiles, la ? atoi(la) : kRangeL2Ahead);
+    const int grid = (int)(tiles < (long long)capped_per_sm(p, per_sm) * sm_count() ? tiles : (long long)capped_per_sm(p, per_sm) * sm_count());
+    k<<<grid, NW * 32, bytes, st>>>(p, adc, rs, (int)tiles);
     return cudaGetLastError();
 }
 
@@ -741,8 +722,6 @@ static cudaError_t run_range(const PlanDev &p, const int16_t *adc, float2 *rs, i
     return run_range_t<N, R1, R2, BT, NW, PAIR, true, 0, NSTAGE>(p, adc, rs, n_frames, st);
 }
 
-static int variant(const char *name);
-
 template <int N, int R1, int R2, int BT, int NW, bool PAD, int SPT, int NSTAGE, bool INPLACE>
 static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
@@ -756,7 +735,7 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     const long long tiles = (long long)n_frames * (p.Sp / BT);
-    const int grid = (int)(tiles < (long long)capped_per_sm(per_sm) * sm_count() ? tiles : (long long)capped_per_sm(per_sm) * sm_count());
+    const int grid = (int)(tiles < (long long)capped_per_sm(p, per_sm) * sm_count() ? tiles : (long long)capped_per_sm(p, per_sm) * sm_count());
     k<<<grid, NW * 32, bytes, st>>>(p, rs, cube, pmap, (int)tiles);
     return cudaGetLastError();
 }
@@ -776,7 +755,7 @@ static cudaError_t run_doppler_warp_t(const PlanDev &p, const float2 *rs, float 
     }
     const long long tiles = (long long)n_frames * (p.Sp / L::kRows);
     const long long want = (tiles + NW - 1) / NW;
-    const int grid = (int)(want < (long long)capped_per_sm(per_sm) * sm_count() ? want : (long long)capped_per_sm(per_sm) * sm_count());
+    const int grid = (int)(want < (long long)capped_per_sm(p, per_sm) * sm_count() ? want : (long long)capped_per_sm(p, per_sm) * sm_count());
     k<<<grid, NW * 32, bytes, st>>>(p, rs, pmap, (int)tiles);
     return cudaGetLastError();
 }
@@ -802,12 +781,6 @@ static cudaError_t run_doppler(const PlanDev &p, const float2 *rs, float2 *cube,
     return run_doppler_t<N, R1, R2, BT, NW, true, 0, NSTAGE, INPLACE>(p, rs, cube, pmap, n_frames, st);
 }
 
-static int variant(const char *name)
-{
-    const char *v = getenv(name);
-    return v ? atoi(v) : 0;
-}
-
 bool plan_supported(int Sp, int Cp, const char **why)
 {
     auto ok = [](int n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; };
@@ -816,7 +789,7 @@ bool plan_supported(int Sp, int Cp, const char **why)
     return true;
 }
 
-// Tile shapes (rows per tile BT, warps per CTA NW) were chosen by sweeping on a B200 (profiles/tune_r1.md):
+// Tile shapes (rows per tile BT, warps per CTA NW) were chosen by sweeping on a B200 (profiles/experiments/README.md):
 // BT = 16 keeps two CTAs resident per SM, which hides the barrier between the two passes better than one
 // CTA with BT = 32.  The radices must match plan_radices().
 cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
@@ -832,32 +805,29 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     // needs 203 KB, one CTA of 16 warps per SM, and loses more to the barrier between the passes than the stores gain (0.224 ->
     // 0.238 ms).  MMW_K1_VARIANT = 5 / 6 force 32- / 16-row tiles (profiles/experiments/r1_k1_tile_height.log).
     case 256:
-        if (variant("MMW_K1_VARIANT") == 6) return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
+        if (p.k1_variant == 6) return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
         return run_range<256, 16, 16, 32, 8, true, 128, 0, 1, 16, 4>(p, adc, rs, n_frames, st);
     case 512:
-        if (variant("MMW_K1_VARIANT") == 5) return run_range<512, 16, 32, 32, 16, true, 256, 0, 1, 8, 4>(p, adc, rs, n_frames, st);
+        if (p.k1_variant == 5) return run_range<512, 16, 32, 32, 16, true, 256, 0, 1, 8, 4>(p, adc, rs, n_frames, st);
         return run_range<512, 16, 32, 16, 8, true, 256, 0, 1, 8, 4>(p, adc, rs, n_frames, st);
     // 1024 points: a 16-row tile needs 209 KB (one CTA per SM).  With 8 warps it lost 2.4 % to 8-row tiles at two CTAs per SM
     // (profiles/experiments/r1_cfg4_tile_sweep.log); with 16 warps it wins 1-4 % (64-byte store pieces are the worst case of
     // profiles/membench_r1.txt: 4.2 TB/s), profiles/experiments/r1_k1_tile_height.log.  MMW_K1_VARIANT = 6: the 8-row shape.
     case 1024:
-        if (variant("MMW_K1_VARIANT") == 6) return run_range<1024, 32, 32, 8, 8, false, 512, 0, 1, 4, 4>(p, adc, rs, n_frames, st);
+        if (p.k1_variant == 6) return run_range<1024, 32, 32, 8, 8, false, 512, 0, 1, 4, 4>(p, adc, rs, n_frames, st);
         return run_range<1024, 32, 32, 16, 16, false, 512, 0, 1, 4, 4>(p, adc, rs, n_frames, st);
     default:   return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_doppler_fft(const PlanDev &plan, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
+// (walking the batch from its last frame to its first, so that K2 starts on what K1 wrote last, changed nothing:
+// profiles/experiments/r1_k2_frame_order.log)
+cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st)
 {
-    PlanDev p = plan;
-    {   // MMW_K2_REVERSE = 0: first frame first (profiles/experiments/r1_k2_frame_order.log)
-        const char *e = getenv("MMW_K2_REVERSE");
-        p.k2_last_frame_first = e ? atoi(e) : kK2LastFrameFirst;
-    }
     switch (p.Cp) {
     case 64:   return run_doppler<64, 8, 8, 16, 4, 0, 0>(p, rs, cube, pmap, n_frames, st);
     case 128: {
-        const int v = variant("MMW_K2_VARIANT");
+        const int v = p.k2_variant;
         // tile-shape experiments kept selectable for profiles/sweep_variants.py (results: profiles/experiments/)
         // warp-private tiles (K2w) are slower at 128 points (4 rows x 8 lanes, two butterflies per thread): 0.222 vs 0.207 ms
         if (v == 11 && !cube) return run_doppler_warp<128, 8, 16, 8, 256, 2>(p, rs, pmap, n_frames, st);
@@ -866,7 +836,7 @@ cudaError_t launch_doppler_fft(const PlanDev &plan, const float2 *rs, float2 *cu
         return run_doppler<128, 8, 16, 16, 4, 256, 128>(p, rs, cube, pmap, n_frames, st);
     }
     case 256: {
-        const int v = variant("MMW_K2_VARIANT");
+        const int v = p.k2_variant;
         if (v == 1) return run_doppler<256, 16, 16, 8, 4, 512, 0, 2>(p, rs, cube, pmap, n_frames, st);
         if (v == 6) return run_doppler<256, 16, 16, 16, 8, 512, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
         if (v == 10 && !cube) return run_doppler_warp<256, 16, 16, 8, 512, 3>(p, rs, pmap, n_frames, st);

@@ -74,6 +74,14 @@ int mmw_legacy_copy_spectrum(float *out);
 /* Releases the lazily created device state (also done at process exit). */
 void mmw_legacy_shutdown(void);
 
+/* Optional configuration of the legacy path (the reference has none: acceleration.cu:7-15 are compile-time defines).
+ * kernel_variant: 0 = pick by batch size (default), 1 = always one CTA per frame, 2 = always the 8-CTA cluster kernel;
+ * quiet != 0 silences cudaProcessing's per-call "Inner CUDA Timing" line (acceleration.cu:533).  A negative value keeps
+ * the current setting.  Without this call the environment (MMW_LEGACY_VARIANT, MMW_LEGACY_QUIET) is read once, at first use.
+ * The device state binds to the CUDA device that is current at the first processing call; later calls make that
+ * device current again.  All legacy entry points serialise on one mutex. */
+int mmw_legacy_configure(int kernel_variant, int quiet);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,7 +72,7 @@ typedef struct mmw_config {
     int cfar_guard_r, cfar_guard_d;   /* guard half-widths (range, Doppler) */
     int cfar_train_r, cfar_train_d;   /* training half-widths beyond the guard */
     float cfar_alpha;       /* detect iff P > alpha * mean(training cells) */
-    int max_det_per_frame;  /* capacity of each frame's detection list (<= 8192) */
+    int max_det_per_frame;  /* capacity of each frame's detection list (<= 65536; max_frames * this <= 2^28) */
     int keep_doppler_cube;  /* 1: write the full Doppler cube to HBM (mmw_copy_doppler_cube works);
                                0: fused — the angle stage re-derives only the detected cells */
     float lambda_over_d;    /* wavelength / element spacing, 2.0 for a half-wavelength array */
@@ -109,8 +109,10 @@ int mmw_set_base_frame(mmw_ctx *ctx, const int16_t *base_host);
 int mmw_set_frame_offset(mmw_ctx *ctx, uint32_t first_frame);
 
 /* CUDA-graph mode for launch-bound use (one or a few frames per call, e.g. per-sensor streaming): the launch sequence
- * of a batch is captured once per distinct (capture address, n_frames, frame offset, base frame, stream) and replayed
- * with a single cudaGraphLaunch.  Off by default; results are identical either way. */
+ * of a batch is captured once per distinct (capture address, n_frames, base frame, stream) and replayed with a single
+ * cudaGraphLaunch.  The frame offset is not part of that key: a new value is patched into the instantiated graph
+ * (one kernel-node parameter update on the host), so a stream of frames with advancing indices replays one graph.
+ * Off by default; results are identical either way. */
 int mmw_set_graph_mode(mmw_ctx *ctx, int enable);
 
 /* The CUDA stream every call of this context runs on (a cudaStream_t). */
@@ -167,7 +169,8 @@ int mmw_merge_gathered(mmw_ctx *ctx, const void *gathered_dev, int n_ranks, long
  * k+1 overlaps the H2D copy and kernels of batch k.  mmw_detection.frame counts from the start of the FILE.
  * A trailing partial frame is zero-filled and processed (the reference passes the short count on and processes the
  * frame anyway, cudaBenchMarking.cpp:374-377).  use_first_as_base != 0: the first frame read becomes the base frame
- * (mmw_set_base_frame) and is not itself processed — the reference's cudaTiming() convention (:357-365).
+ * (mmw_set_base_frame) and is not itself processed — the reference's cudaTiming() convention (:357-365); it replaces any
+ * base frame set before and STAYS installed after the call returns (mmw_set_base_frame(ctx, NULL) turns it off).
  * *n_frames_done receives the number of frames processed.  Returns MMW_OK, MMW_ERR_OVERFLOW (list truncated) or an
  * error (MMW_ERR_ARG if the file cannot be opened). */
 int mmw_process_capture_file(mmw_ctx *ctx, const char *path, long long first_frame, int max_frames, int use_first_as_base,

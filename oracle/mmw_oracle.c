@@ -310,6 +310,9 @@ static void scratch_free(orc_scratch *w)
 
 /* one frame; per-thread scratch is reused across frames (the caller's optional output buffers win) */
 static const int16_t *g_base_frame = NULL;   /* set by orc_process_frames_base for the duration of the call */
+static double *g_angle_ratio = NULL;         /* set by orc_process_frames_ratio: per detection, 2nd-largest / largest angle-bin power */
+
+static const orc_detection *g_dets0 = NULL;  /* start of the caller's detection buffer (index base of g_angle_ratio) */
 
 static long process_one(const int16_t *adc, int f, int S, int C, int A,
                         const float *win_r, const float *win_d,
@@ -341,8 +344,10 @@ static long process_one(const int16_t *adc, int f, int S, int C, int A,
             ++tot;
             if (n >= cap) continue;
             for (int a = 0; a < A; ++a) x[a] = dc[(long)a * M + m];
-            int k = orc_angle_argmax(x, A, n_theta, NULL);
+            double ratio = 0;
+            int k = orc_angle_argmax(x, A, n_theta, &ratio);
             int kw = k < n_theta / 2 ? k : k - n_theta;
+            if (g_angle_ratio) g_angle_ratio[(dets - g_dets0) + n] = ratio;
             orc_detection *o = &dets[n++];
             o->frame = (uint32_t)f;
             o->range_bin = (uint16_t)r;
@@ -370,6 +375,7 @@ long orc_process_frames(const int16_t *adc, int n_frames, int S, int C, int A,
     /* every frame gets an equal slice of the caller's buffer so that frames can
      * run in parallel; slices are compacted afterwards, preserving frame order */
     const long per = n_frames > 0 ? det_cap / n_frames : 0;
+    g_dets0 = dets;
     long *cnt = (long *)calloc((size_t)(n_frames > 0 ? n_frames : 1), sizeof(long));
     long *tot = (long *)calloc((size_t)(n_frames > 0 ? n_frames : 1), sizeof(long));
     if (n_threads < 1) n_threads = 1;
@@ -394,8 +400,10 @@ long orc_process_frames(const int16_t *adc, int n_frames, int S, int C, int A,
     }
     long n = 0, t = 0;
     for (int f = 0; f < n_frames; ++f) {
-        if (n != (long)f * per && cnt[f] > 0)
+        if (n != (long)f * per && cnt[f] > 0) {
             memmove(dets + n, dets + (long)f * per, (size_t)cnt[f] * sizeof(orc_detection));
+            if (g_angle_ratio) memmove(g_angle_ratio + n, g_angle_ratio + (long)f * per, (size_t)cnt[f] * sizeof(double));
+        }
         n += cnt[f];
         t += tot[f];
     }
@@ -418,5 +426,22 @@ long orc_process_frames_base(const int16_t *adc, const int16_t *base, int n_fram
     long n = orc_process_frames(adc, n_frames, S, C, A, win_r, win_d, p, lambda_over_d, dets, det_cap, n_total,
                                 rs_out, dc_out, P_out, mask_out, noise_out, n_threads);
     g_base_frame = NULL;
+    return n;
+}
+
+/* orc_process_frames_base that also reports, per detection written, the ratio of the second-largest to the largest bin of
+ * its angle spectrum (angle_ratio[det_cap]; lets a checker skip near-tie arg-maxes without keeping the whole Doppler
+ * cube); not re-entrant */
+long orc_process_frames_ratio(const int16_t *adc, const int16_t *base, int n_frames, int S, int C, int A,
+                              const float *win_r, const float *win_d,
+                              const orc_cfar_params *p, double lambda_over_d,
+                              orc_detection *dets, long det_cap, long *n_total,
+                              orc_cx *rs_out, orc_cx *dc_out, double *P_out,
+                              uint8_t *mask_out, double *noise_out, int n_threads, double *angle_ratio)
+{
+    g_angle_ratio = angle_ratio;
+    long n = orc_process_frames_base(adc, base, n_frames, S, C, A, win_r, win_d, p, lambda_over_d, dets, det_cap, n_total,
+                                     rs_out, dc_out, P_out, mask_out, noise_out, n_threads);
+    g_angle_ratio = NULL;
     return n;
 }

@@ -114,6 +114,16 @@ long orc_process_frames_base(const int16_t *adc, const int16_t *base, int n_fram
                              uint8_t *mask_out, double *noise_out,
                              int n_threads);
 
+/* same, also reporting per detection written the ratio 2nd-largest / largest bin power of its angle spectrum
+ * (angle_ratio[det_cap], aligned with dets[]); lets a checker skip near-tie arg-maxes without the whole Doppler cube */
+long orc_process_frames_ratio(const int16_t *adc, const int16_t *base, int n_frames, int S, int C, int A,
+                              const float *win_r, const float *win_d,
+                              const orc_cfar_params *p, double lambda_over_d,
+                              orc_detection *dets, long det_cap, long *n_total,
+                              orc_cx *rs_out, orc_cx *dc_out, double *P_out,
+                              uint8_t *mask_out, double *noise_out,
+                              int n_threads, double *angle_ratio);
+
 #ifdef __cplusplus
 }
 #endif

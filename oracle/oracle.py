@@ -99,6 +99,8 @@ def lib():
         ]
         L.orc_process_frames_base.restype = C.c_long
         L.orc_process_frames_base.argtypes = [_vp] + L.orc_process_frames.argtypes
+        L.orc_process_frames_ratio.restype = C.c_long
+        L.orc_process_frames_ratio.argtypes = L.orc_process_frames_base.argtypes + [_vp]
         _lib = L
     return _lib
 
@@ -183,7 +185,8 @@ def angle_fft_size(A: int) -> int:
 
 def process_frames(adc, n_frames, S, C_, A, win_r, win_d, guard=(2, 2), train=(8, 4), alpha=15.0,
                    lambda_over_d=2.0, det_cap_per_frame=4096, want=(), n_threads=1, base=None):
-    """Whole chain.  `want` may name 'rs', 'dc', 'P', 'mask', 'noise' to get the intermediates.
+    """Whole chain.  `want` may name 'rs', 'dc', 'P', 'mask', 'noise' to get the intermediates, and 'ratio' for the
+    per-detection ratio 2nd-largest / largest angle-bin power (out['ratio'], aligned with out['dets']).
     base: one frame (int16, capture format) subtracted from every frame before the range window, or None."""
     adc = np.ascontiguousarray(adc, np.int16)
     base = None if base is None else np.ascontiguousarray(base, np.int16).reshape(-1)
@@ -202,13 +205,16 @@ def process_frames(adc, n_frames, S, C_, A, win_r, win_d, guard=(2, 2), train=(8
     if "noise" in want:
         out["noise"] = np.empty((n_frames, Sp, Cp), np.float64)
     total = C.c_long(0)
-    n = lib().orc_process_frames_base(
+    ratio = np.zeros(dets.size, np.float64) if "ratio" in want else None
+    n = lib().orc_process_frames_ratio(
         _ptr(adc), _ptr(base), n_frames, S, C_, A,
         _ptr(np.ascontiguousarray(win_r, np.float32)), _ptr(np.ascontiguousarray(win_d, np.float32)),
         C.byref(prm), float(lambda_over_d), _ptr(dets), dets.size, C.byref(total),
         _ptr(out.get("rs")), _ptr(out.get("dc")), _ptr(out.get("P")), _ptr(out.get("mask")), _ptr(out.get("noise")),
-        int(n_threads),
+        int(n_threads), _ptr(ratio),
     )
+    if ratio is not None:
+        out["ratio"] = ratio[:n].copy()
     out["dets"] = dets[:n].copy()
     out["n_total"] = total.value
     return out

@@ -9,6 +9,9 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-4          # relative to the maximum of the array being compared
 NEAR = 1e-5         # |P - thr| <= NEAR * thr  -> cell is "at threshold", excluded from the bit-exact claim
+# CA-CFAR noise estimate (mean of the training cells) relative to the oracle's: the fp32 window sum only ever adds (~1e-6),
+# the rest is the fp32 FFT error of the near-floor cells it averages; measured <= 1.05e-5 on B200 (tests/test_gpu_bench_paths.py)
+NOISE_RTOL = 5e-5
 
 # the next three exercise the 256-point angle FFT (A > 64: the cfg4 imaging array), an odd antenna count and the maximum A
 SHAPES = [(64, 64, 2), (100, 128, 4), (128, 64, 12), (256, 128, 4), (512, 256, 12), (1024, 64, 2), (64, 1024, 1), (256, 512, 3),
@@ -101,7 +104,7 @@ def test_cfar_and_detections(pkg, orc, cases, shape, keep):
             continue
         o = by[k]
         assert abs(d["power"] - o["power"]) <= TOL * ref["P"][k[0]].max()
-        assert abs(d["noise"] - o["noise"]) <= 1e-3 * o["noise"] + TOL * 1e-3 * ref["P"][k[0]].max()
+        assert abs(d["noise"] - o["noise"]) <= NOISE_RTOL * o["noise"]
         x = ref["dc"][k[0]][:, k[1], k[2]]
         _, ratio = orc.angle_argmax(x, n_theta)
         if ratio < 1 - 1e-4:                                   # angle arg-max not a near tie
@@ -136,7 +139,7 @@ def test_cfar_geometries(pkg, orc, guard, train, alpha):
     for d in dets:
         k = (int(d["frame"]), int(d["range_bin"]), int(d["doppler_bin"]))
         if k in by:
-            assert abs(d["noise"] - by[k]["noise"]) <= 1e-3 * by[k]["noise"] + 1e-7 * ref["P"][k[0]].max()
+            assert abs(d["noise"] - by[k]["noise"]) <= NOISE_RTOL * by[k]["noise"]
 
 
 @pytest.mark.parametrize("variant", [1, 22, 42, 82, 23, 43, 83, 24, 44, 84])
@@ -164,7 +167,7 @@ def test_cfar_kernel_forms_agree_with_oracle(pkg, orc, cases, variant, monkeypat
         k = (int(d["frame"]), int(d["range_bin"]), int(d["doppler_bin"]))
         if k in by:
             hit += 1
-            assert abs(d["noise"] - by[k]["noise"]) <= 1e-3 * by[k]["noise"] + TOL * 1e-3 * ref["P"][k[0]].max()
+            assert abs(d["noise"] - by[k]["noise"]) <= NOISE_RTOL * by[k]["noise"]
     assert hit >= len(dets) - int(near.sum())
 
 
@@ -237,10 +240,19 @@ def test_user_windows_round_trip(pkg, orc):
 
 
 # ---------------------------------------------------------------- legacy path (reference cfg 100 x 128 x 4)
+@pytest.fixture
+def legacy_kernel(pkg):
+    """forces one form of the legacy frame kernel for the test (mmw_legacy_configure), restores the default afterwards"""
+    def pick(name):
+        pkg.api.legacy_configure(kernel_variant={"single_cta": 1, "cluster": 2}[name], quiet=1)
+    yield pick
+    pkg.api.legacy_configure(kernel_variant=0)
+
+
 @pytest.mark.parametrize("kernel", ["cluster", "single_cta"])
-def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir, kernel, monkeypatch):
-    """both forms of the legacy frame kernel: the 8-CTA cluster (default) and the single-CTA kernel (MMW_LEGACY_VARIANT=1)"""
-    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "2")
+def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir, kernel, legacy_kernel):
+    """both forms of the legacy frame kernel: the 8-CTA cluster (default for single frames) and the single-CTA kernel"""
+    legacy_kernel(kernel)
     gold = np.load(f"{golden_dir}/legacy_reference.npz")
     i = 0
     timers = np.zeros(4)
@@ -263,8 +275,8 @@ def test_legacy_matches_golden_and_oracle(pkg, orc, golden_dir, kernel, monkeypa
 
 
 @pytest.mark.parametrize("kernel", ["cluster", "single_cta"])
-def test_legacy_full_spectrum_and_edges(pkg, orc, kernel, monkeypatch):
-    monkeypatch.setenv("MMW_LEGACY_VARIANT", "1" if kernel == "single_cta" else "2")
+def test_legacy_full_spectrum_and_edges(pkg, orc, kernel, legacy_kernel):
+    legacy_kernel(kernel)
     cap = pkg.synth.legacy_capture(3, seed=21)
     base = orc.reshape(cap[0], 100, 128, 4)[:12800]
     d_ref, raw_ref, spec_ref = orc.legacy_frame(cap[2], base, want_spectrum=True)
@@ -285,6 +297,38 @@ def test_legacy_full_spectrum_and_edges(pkg, orc, kernel, monkeypatch):
     frame = pkg.synth.pack_iiqq(z).reshape(-1)
     zero_base = np.zeros(12800, complex)
     assert pkg.api.legacy_process_frame(frame, zero_base) == orc.legacy_frame(frame, zero_base)
+
+
+@pytest.mark.parametrize("kernel", ["cluster", "single_cta"])
+def test_legacy_many_near_tie_bins(pkg, orc, kernel, legacy_kernel):
+    """More near-tie bins than any fixed-size candidate list would hold: 60 equal-amplitude tones whose 12 800-sample
+    windows are mutually orthogonal (bins are multiples of 32 = 25 * 16384 / 12800), so the 60 peaks of the 16 384-point
+    spectrum agree to ~1e-5 (int16 rounding noise; the top two differ by 2e-7 .. 7e-6) — inside the 1e-4 near-tie window
+    of the fp32 pass and at or below its rounding error, far outside fp64 rounding.
+    The fp64 re-check must visit all of them in ascending bin order and return the reference's first maximum
+    (cudaBenchMarking.cpp:191-206).  Also: a flat spectrum (an impulse at sample 0: every bin exactly 1) -> bin 0."""
+    legacy_kernel(kernel)
+    k = np.arange(100 * 128)
+    zero_base = np.zeros(12800, complex)
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        bins = 32 * (2 + rng.permutation(200)[:60])                      # 60 distinct multiples of 32 below 0.4 * 16384
+        ph = rng.uniform(0, 2 * np.pi, 60)
+        x = sum(1000.0 * np.exp(2j * np.pi * (b / 16384.0) * k + 1j * p) for b, p in zip(bins, ph))
+        z = np.zeros((128, 4, 100), complex)
+        z[:, 0, :] = x.reshape(128, 100)
+        frame = pkg.synth.pack_iiqq(z).reshape(-1)
+        d_ref, raw_ref, spec = orc.legacy_frame(frame, zero_base, want_spectrum=True)
+        mag = np.abs(spec[:6553]) ** 2
+        n_near = int((mag >= mag.max() * (1 - 1e-4)).sum())
+        assert n_near > 32, n_near                                       # the case the old 32-entry list gave up on
+        assert pkg.api.legacy_process_frame(frame, zero_base) == (d_ref, raw_ref), (seed, n_near)
+        assert raw_ref in bins
+    z = np.zeros((128, 4, 100), complex)
+    z[0, 0, 0] = 1000.0
+    frame = pkg.synth.pack_iiqq(z).reshape(-1)
+    assert orc.legacy_frame(frame, zero_base) == (0.0, 0)
+    assert pkg.api.legacy_process_frame(frame, zero_base) == (0.0, 0)
 
 
 def test_legacy_upload_paths_and_short_frames(pkg, orc):
@@ -329,7 +373,7 @@ def test_chain_matches_numpy_golden_fixture(pkg, golden_dir):
                     if near[r, d]:
                         continue
                     rec = by[(int(r), int(d))]
-                    assert abs(rec["noise"] - nz) <= 1e-3 * nz + TOL * 1e-3 * P.max()
+                    assert abs(rec["noise"] - nz) <= NOISE_RTOL * nz
                     if not tie:
                         assert rec["angle_bin"] == ab
                     n_checked += 1
