@@ -410,6 +410,12 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
     ms = max(ms_by_rank)
     frame_counts = ctx.read_counts(F)                       # true per-frame hit counts of this rank's last batch
     hdr = header_view.view(torch.int32).cpu().numpy()
+    # wide arrays in fused mode re-transform every (frame, range bin) that has hits (doppler_extract_kernel): those rows of the
+    # range spectrum are read once more, A * C * 8 bytes each
+    hit_rows = 0
+    if A >= 32 and not keep_cube and int(ctx.info.kernels_per_batch) == 7:
+        last = pkg.sharding.records_from_bytes(pkg.sharding.device_bytes_view(dense_ptr, 24 * int(hdr[0]), dev), pkg.DET_DTYPE)
+        hit_rows = len(np.unique(last["frame"].astype(np.int64) << 16 | last["range_bin"]))
     local_overflow = int(hdr[3]) or int(frame_counts.max() > max_det)
     if world == 1:
         n_det_step, gather_overflow = int(hdr[0]), 0
@@ -431,7 +437,7 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
         F * (4 * N_adc + 8 * A * ctx.Sp * C),                   # K1: int16 IQ in, range spectrum out
         F * (8 * A * ctx.Sp * C + (8 * N if keep_cube else 0) + 4 * M),   # K2: spectrum in, (cube +) power map out
         F * (4 * M + M // 8),                                   # K3: power map in, bit mask out
-        F * (M // 8),                                           # K4a+K4b: mask in (+ D records)
+        F * (M // 8) + hit_rows * A * C * 8,                    # K4: mask in, hit rows of the range spectrum once more (wide arrays), records out
     ]
 
     # ---- end to end through the host-facing API: pinned host capture -> H2D -> chain -> D2H list ----
@@ -470,7 +476,7 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
         fps=world * F * K / (ms * 1e-3), ms=ms, ms_by_rank=ms_by_rank, host_ms_by_rank=host_ms_by_rank,
         host_split=list(host_split), total_ms_one=total_ms / iters, stage_ms=stage_ms, stage_bytes=stage_bytes,
         b_alg=int(ctx.info.algorithmic_bytes_per_frame), kernels_per_batch=int(ctx.info.kernels_per_batch),
-        n_det_step=n_det_step, max_det_frame=int(frame_counts.max()), max_det=max_det, overflow=overflow,
+        n_det_step=n_det_step, max_det_frame=int(frame_counts.max()), max_det=max_det, overflow=overflow, hit_rows=hit_rows,
         gather_records=gather_records, gather_overflow=gather_overflow,
         e2e_fps=world * F * e2e_steps / t_e2e, e2e_steps=e2e_steps, e2e_dets=len(dets), e2e_two=len(e2e_ring) > 1,
         h2d_bytes=F * 4 * N_adc, N_adc=N_adc,
@@ -501,7 +507,7 @@ def compact_chain(res, world):
         "e2e": {"value": res["e2e_fps"], "unit": "frames/s", "h2d_bytes_per_step": res["h2d_bytes"],
                 "d2h_bytes_per_step": 32 + 24 * res["e2e_dets"], "steps": res["e2e_steps"]},
         "detections_per_step": res["n_det_step"], "max_detections_in_one_frame": res["max_det_frame"],
-        "max_det_per_frame": res["max_det"], "overflow": res["overflow"],
+        "max_det_per_frame": res["max_det"], "overflow": res["overflow"], "hit_rows_retransformed": res["hit_rows"] or None,
         "exchange_records_per_rank": res["gather_records"] if world > 1 else None,
         "config_index": w["idx"],
     }
@@ -557,7 +563,7 @@ def run_chain(args, env):
                 "host_issue_split_ms_per_step_rank0": {"process_device": res["host_split"][0] / K * 1e3, "exchange": res["host_split"][1] / K * 1e3},
                 "rank0_numa_node": env.numa,
                 "detections_per_step": res["n_det_step"], "max_detections_in_one_frame": res["max_det_frame"],
-                "max_det_per_frame": res["max_det"], "overflow": res["overflow"],
+                "max_det_per_frame": res["max_det"], "overflow": res["overflow"], "hit_rows_retransformed": res["hit_rows"] or None,
             },
             "roofline": {
                 "bound": "hbm", "kernel": STAGE_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -65,6 +65,8 @@ struct mmw_ctx {
     uint32_t *d_counts;
     uint32_t *d_offsets;
     unsigned int *d_ticket;
+    uint4 *d_rows;            // hit rows of the selective Doppler re-FFT (wide arrays, fused mode)
+    float2 *d_snap;           // antenna snapshots of the detected cells (same path)
     unsigned char *d_result;  // [32-byte header | dense ordered detection list]: one D2H usually moves both
     mmw_detection *d_dense;
     uint32_t *d_header;
@@ -95,6 +97,7 @@ struct mmw_ctx {
         cudaGraphExec_t exec;
         cudaGraphNode_t record_node;  // the kernel node whose PlanDev carries frame_offset (nullptr: none found)
         cudaKernelNodeParams record_kp;   // its launch parameters as captured (the argument pointers point into `graph`)
+        int record_args;              // its argument count
         uint32_t frame_offset;        // value `exec` currently holds
     };
     std::map<std::tuple<const void *, int, const void *, void *>, GraphEntry> *graphs;
@@ -194,7 +197,7 @@ void mmw_destroy(mmw_ctx *c)
     cudaSetDevice(c->device);
     cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
     cudaFree(c->d_adc); cudaFree(c->d_base); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_psplit); cudaFree(c->d_mask);
-    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_result); cudaFree(c->d_scratch);
+    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_rows); cudaFree(c->d_snap); cudaFree(c->d_result); cudaFree(c->d_scratch);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto &h : c->h_ring) if (h) cudaFreeHost(h);
     for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
@@ -272,9 +275,15 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     if ((rc = dev_alloc(c, &c->d_keys, (size_t)F * cfg->max_det_per_frame))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_counts, (size_t)F))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_offsets, (size_t)F + 1))) return fail(rc);
-    if ((rc = dev_alloc(c, &c->d_ticket, (size_t)2))) return fail(rc);
-    if (cudaMemset(c->d_ticket, 0, 2 * sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
+    if ((rc = dev_alloc(c, &c->d_ticket, (size_t)4))) return fail(rc);
+    if (cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     c->dense_cap = F * cfg->max_det_per_frame;
+    // wide arrays without a Doppler cube: snapshots of the detected cells come from a selective re-FFT of the hit rows
+    // (launch_detect); its buffers scale with the detection capacity — beyond 2 GB the per-detection kernel is used instead
+    if (A >= 32 && !cfg->keep_doppler_cube && (size_t)c->dense_cap * A * sizeof(float2) <= ((size_t)2 << 30)) {
+        if ((rc = dev_alloc(c, &c->d_rows, (size_t)F * Sp))) return fail(rc);
+        if ((rc = dev_alloc(c, &c->d_snap, (size_t)c->dense_cap * A))) return fail(rc);
+    }
     const size_t result_bytes = kResultHeaderBytes + (size_t)c->dense_cap * sizeof(mmw_detection);
     if ((rc = dev_alloc(c, &c->d_result, result_bytes))) return fail(rc);
     c->d_header = reinterpret_cast<uint32_t *>(c->d_result);
@@ -335,7 +344,8 @@ int mmw_get_info(const mmw_ctx *c, mmw_info *info)
     const long long N = (long long)p.Sp * p.Cp * p.A, M = (long long)p.Sp * p.Cp;
     info->algorithmic_bytes_per_frame = 28 * N + 8 * M;
     info->workspace_bytes = (long long)c->workspace_bytes;
-    info->kernels_per_batch = 5;
+    // K1, K2, K3, list, measure; the selective re-FFT path of wide arrays runs rows + extract + angle instead of measure
+    info->kernels_per_batch = (c->d_snap != nullptr && p.k4_variant != 1) ? 7 : 5;
     return MMW_OK;
 }
 
@@ -433,7 +443,7 @@ static int run_back(mmw_ctx *c, int n_frames, cudaEvent_t *stage_ev)
     DetectBuffers b;
     b.rs = c->d_rs; b.cube = c->d_cube; b.pmap = c->d_pmap; b.noise_map = c->d_noise; b.mask = c->d_mask;
     b.keys = c->d_keys; b.counts = c->d_counts; b.offsets = c->d_offsets; b.header = c->d_header;
-    b.ticket = c->d_ticket; b.dense = c->d_dense;
+    b.ticket = c->d_ticket; b.dense = c->d_dense; b.rows = c->d_rows; b.snap = c->d_snap;
     CK(launch_detect(p, b, n_frames, c->dense_cap, c->sm_count, c->stream));
     if (stage_ev) CK(cudaEventRecord(stage_ev[4], c->stream));
     c->last_frames = n_frames;
@@ -489,7 +499,8 @@ static int run_batch_graphed(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
                     cudaKernelNodeParams kp;
                     if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
                     if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
-                    if (is_record_kernel(kp.func)) { ge.record_node = nodes[i]; ge.record_kp = kp; }
+                    const int n_args = record_kernel_args(kp.func);
+                    if (n_args > 0) { ge.record_node = nodes[i]; ge.record_kp = kp; ge.record_args = n_args; }
                 }
         }
         cudaGetLastError();
@@ -501,8 +512,8 @@ static int run_batch_graphed(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
         cudaKernelNodeParams kp = ge.record_kp;
         PlanDev patched = *reinterpret_cast<const PlanDev *>(kp.kernelParams[0]);       // argument 0 of both record kernels
         patched.frame_offset = c->plan.frame_offset;
-        void *args[kRecordKernelArgs];
-        for (int i = 0; i < kRecordKernelArgs; ++i) args[i] = kp.kernelParams[i];
+        void *args[kRecordKernelMaxArgs];
+        for (int i = 0; i < ge.record_args; ++i) args[i] = kp.kernelParams[i];
         args[0] = &patched;
         kp.kernelParams = args;
         CK(cudaGraphExecKernelNodeSetParams(ge.exec, ge.record_node, &kp));

@@ -110,15 +110,21 @@ struct DetectBuffers {
     uint32_t *counts;       // [F]    true hit count per frame
     uint32_t *offsets;      // [F+1]  exclusive scan of min(count, max_det)
     uint32_t *header;       // {n_written, n_total, n_frames, overflow}
-    unsigned int *ticket;   // [0] last-CTA-done counter of list_kernel, [1] work cursor of measure_kernel (both self-resetting)
+    unsigned int *ticket;   // [0] last-CTA-done counter of list_kernel, [1] work cursor of measure_kernel, [2] hit-row count (all self-resetting)
     mmw_detection *dense;   // ordered detection list of the batch
+    // wide arrays in fused mode (A >= 32, no Doppler cube): the selective Doppler re-FFT path (nullptr: measure_wide_kernel instead)
+    uint4 *rows;            // [F * Sp] {frame, range bin, dense index of the row's first hit, -}: every (frame, range bin) with hits
+    float2 *snap;           // [dense capacity][A] antenna snapshots of the detected cells
 };
 cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, float *noise_map, int n_frames, int sm_count, cudaStream_t st);
 cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st);
 // the kernels that write mmw_detection records (the only readers of PlanDev.frame_offset, their argument 0): graph mode patches
-// that argument in place instead of re-capturing when the frame offset changes (mmw_api.cu)
-constexpr int kRecordKernelArgs = 12;
-bool is_record_kernel(const void *func);
+// that argument in place instead of re-capturing when the frame offset changes (mmw_api.cu).  Returns the kernel's argument
+// count, 0 if `func` is not one of them.
+constexpr int kRecordKernelMaxArgs = 12;
+int record_kernel_args(const void *func);
+cudaError_t launch_doppler_extract(const PlanDev &p, const float2 *rs, const uint32_t *keys, const uint32_t *offsets, const uint4 *rows,
+                                   const unsigned int *n_rows, float2 *snap, int dense_cap, int max_rows, cudaStream_t st);
 cudaError_t launch_merge(const unsigned char *gathered, int n_ranks, size_t stride_bytes, unsigned char *merged, int merged_cap,
                          cudaStream_t st);
 // export helpers (not on the hot path): internal layout -> the canonical layouts of mmw_radar.h

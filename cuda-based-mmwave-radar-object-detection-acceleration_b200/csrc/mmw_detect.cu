@@ -25,6 +25,7 @@
 // way round (see its header).
 #include <stdlib.h>
 
+#include "fft_regs.cuh"
 #include "mmw_common.cuh"
 
 namespace mmw {
@@ -530,6 +531,7 @@ __global__ void __launch_bounds__(kListNT) list_kernel(PlanDev p, const uint32_t
         header[3] = (true_total != carry || carry > (uint32_t)dense_cap) ? 1u : 0u;
         ticket[0] = 0u;                                         // self-cleaning for the next batch
         ticket[1] = 0u;                                         // work cursor of measure_kernel
+        ticket[2] = 0u;                                         // hit-row count of rows_kernel
     }
 }
 
@@ -924,6 +926,162 @@ __global__ void __launch_bounds__(kMeasNT) measure_wide_kernel(PlanDev p, const 
 }
 
 // ---------------------------------------------------------------------------
+// wide arrays, fused mode: hit rows -> (K2x doppler_extract_kernel, mmw_pipeline.cu) -> angle FFT + records
+// ---------------------------------------------------------------------------
+// rows_kernel: every (frame, range bin) that has at least one detection, found as the heads of the runs of equal range bin
+// in the ordered key list.  The order of `rows` is whatever the atomics give; nothing downstream depends on it (each row is
+// transformed on its own, and a detection's slot in `snap` is its position in the dense list).
+__global__ void __launch_bounds__(256) rows_kernel(PlanDev p, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ offsets,
+                                                   uint4 *__restrict__ rows, unsigned int *__restrict__ n_rows, int n_frames, int dense_cap)
+{
+    const uint32_t total = min(offsets[n_frames], (uint32_t)dense_cap);
+    MeasFrame fc = {0, 0u, 0u};
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        lookup_frame(offsets, n_frames, g, fc);
+        const uint32_t *kf = keys + (size_t)fc.f * p.max_det - fc.fbeg;
+        const uint32_t r = kf[g] >> 16;
+        if (g == fc.fbeg || (kf[g - 1] >> 16) != r) rows[atomicAdd(n_rows, 1u)] = make_uint4((uint32_t)fc.f, r, g, 0u);
+    }
+}
+
+// angle_fft_kernel: the NTH-point angle spectrum of every detection as a real FFT (the per-detection kernels evaluate it as a
+// DFT, NTH * A complex MACs per detection: 0.4 MFLOP at A = 192, more than the rest of the record put together), its arg-max
+// (strict >, first wins), the 3x3 grouping flag and the 24-byte record.  Same scheme as the Doppler kernels: a warp owns its
+// rows outright — lanes = ROWS detections x SUBS butterflies of one detection — the two passes meet in a warp-private
+// shared-memory row, no CTA barrier after the twiddle table is loaded.
+template <int NTH, int R1, int R2>
+struct AngleWarp {
+    static constexpr int kMinR = R1 < R2 ? R1 : R2;
+    static constexpr int kSubs = kMinR > 16 ? 16 : kMinR;
+    static constexpr int kRows = 32 / kSubs;
+    static constexpr int kU1 = R2 / kSubs;
+    static constexpr int kU2 = R1 / kSubs;
+    static constexpr int kRowStride = NTH + R1;                      // float2: NTH points + one pad per run of R2
+    static constexpr int kWarps = 8;
+    static constexpr int kBytes = NTH * 8 + kWarps * kRows * kRowStride * 8;
+    static_assert(kSubs >= 8, "the eight 3x3 neighbours of a detection are tested by eight lanes of its group");
+};
+
+template <int NTH, int R1, int R2>
+__global__ void __launch_bounds__(256) angle_fft_kernel(PlanDev p, const float2 *__restrict__ snap, const float *__restrict__ pmap,
+                                                        const float *__restrict__ noise_map, const uint32_t *__restrict__ mask,
+                                                        const uint32_t *__restrict__ keys, const uint32_t *__restrict__ offsets,
+                                                        mmw_detection *__restrict__ dense, int n_frames, int dense_cap)
+{
+    static_assert(R1 * R2 == NTH, "plan");
+    using L = AngleWarp<NTH, R1, R2>;
+    constexpr int SUBS = L::kSubs, ROWS = L::kRows, U1 = L::kU1, U2 = L::kU2;
+    constexpr int LR1 = ilog2(R1), LR2 = ilog2(R2);
+    extern __shared__ __align__(16) unsigned char smem[];
+    float2 *tw = reinterpret_cast<float2 *>(smem);                   // exp(-2 pi i k / NTH), natural order
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float2 *ring = tw + NTH + (size_t)warp * ROWS * L::kRowStride;
+    const int row = lane / SUBS, sub = lane % SUBS;
+    const int Sp = p.Sp, Cp = p.Cp, A = p.A;
+    for (int i = tid; i < NTH; i += 256) tw[i] = p.tw_a[i];
+    __syncthreads();                                                 // the only CTA-wide barrier
+
+    const uint32_t total = min(offsets[n_frames], (uint32_t)dense_cap);
+    const uint32_t gw = (blockIdx.x * L::kWarps + warp) * ROWS, gstep = gridDim.x * L::kWarps * ROWS;
+    float2 *r = ring + row * L::kRowStride;
+    MeasFrame fc = {0, 0u, 0u};
+#pragma unroll 1
+    for (uint32_t g0 = gw; g0 < total; g0 += gstep) {
+        const uint32_t g = g0 + row;
+        const bool live = g < total;
+        // the snapshot, zero-padded to NTH (coalesced: the SUBS lanes of a group read neighbouring antennas)
+        const float2 *src = snap + (size_t)(live ? g : 0) * A;
+#pragma unroll 4
+        for (int i = sub; i < NTH; i += SUBS) r[i] = (live && i < A) ? src[i] : make_float2(0.f, 0.f);
+        __syncwarp();
+        // pass 1: every input into registers first (the outputs overwrite other threads' inputs)
+        float2 x[U1][R1];
+#pragma unroll
+        for (int u = 0; u < U1; ++u) {
+            const int n2 = sub + u * SUBS;
+#pragma unroll
+            for (int m = 0; m < R1; ++m) x[u][m] = r[n2 + m * R2];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < U1; ++u) {
+            const int n2 = sub + u * SUBS;
+            dft_regs<R1>(x[u]);
+            r[n2] = x[u][0];
+#pragma unroll
+            for (int k1 = 1; k1 < R1; ++k1) r[k1 * (R2 + 1) + n2] = cmul(x[u][bitrev(k1, LR1)], tw[(n2 * k1) & (NTH - 1)]);
+        }
+        __syncwarp();
+        // pass 2 + arg-max of |Y|^2: larger power wins, equal power -> lower bin
+        float best = -1.f;
+        int bestk = 0;
+#pragma unroll
+        for (int u = 0; u < U2; ++u) {
+            const int k1 = sub + u * SUBS;
+            float2 y[R2];
+            const float2 *wi = r + k1 * (R2 + 1);
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) y[n2] = wi[n2];
+            dft_regs<R2>(y);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+                const float2 v = y[bitrev(k2, LR2)];
+                const float m = v.x * v.x + v.y * v.y;
+                const int k = k1 + R1 * k2;
+                if (m > best || (m == best && k < bestk)) { best = m; bestk = k; }
+            }
+        }
+#pragma unroll
+        for (int o = SUBS / 2; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+            if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+        }
+        __syncwarp();                                                // the row is free for the next detection
+        // record: lanes 0..7 of the group look at the eight 3x3 neighbours (Doppler wraps, range clamps; ties -> lowest (r, d))
+        bool worse = false;
+        int f = 0, rb = 0, d = 0;
+        float pw = 0.f, noise = 0.f;
+        if (live) {
+            lookup_frame(offsets, n_frames, g, fc);
+            f = fc.f;
+            const uint32_t key = keys[(size_t)f * p.max_det + (g - fc.fbeg)];
+            rb = (int)(key >> 16);
+            d = (int)(key & 0xffffu);
+            const float *pf = pmap + (size_t)f * Cp * Sp;
+            pw = pf[(size_t)d * Sp + rb];
+            if (sub == 0) noise = noise_map[((size_t)f * Cp + d) * Sp + rb];
+            if (sub < 8) {
+                const int cell = sub < 4 ? sub : sub + 1;
+                const int rr = rb + cell / 3 - 1;
+                const int dd = (d + cell % 3 - 1 + Cp) & (Cp - 1);
+                if (rr >= 0 && rr < Sp) {
+                    const uint32_t w = mask[((size_t)f * (Cp / 32) + (dd >> 5)) * Sp + rr];
+                    if ((w >> (dd & 31)) & 1u) {
+                        const float pn = pf[(size_t)dd * Sp + rr];
+                        const uint32_t kn = ((uint32_t)rr << 16) | (uint32_t)dd;
+                        worse = (pn > pw) || (pn == pw && kn < key);
+                    }
+                }
+            }
+        }
+        const uint32_t wm = __ballot_sync(0xffffffffu, worse);
+        const bool is_peak = ((wm >> (row * SUBS)) & 0xffu) == 0u;
+        if (live && sub == 0) write_record(p, dense, g, f, rb, d, pw, noise, bestk, is_peak);
+    }
+}
+
+template <int NTH, int R1, int R2>
+static cudaError_t run_angle_fft(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st)
+{
+    using L = AngleWarp<NTH, R1, R2>;
+    const long long want = ((long long)dense_cap + L::kWarps * L::kRows - 1) / (L::kWarps * L::kRows);
+    const int grid = (int)(want < (long long)sm_count * 4 ? (want < 1 ? 1 : want) : (long long)sm_count * 4);
+    angle_fft_kernel<NTH, R1, R2><<<grid, 256, L::kBytes, st>>>(p, b.snap, b.pmap, b.noise_map, b.mask, b.keys, b.offsets, b.dense, n_frames, dense_cap);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // merge of gathered per-rank result blocks (rank 0, after the NCCL gather)
 // ---------------------------------------------------------------------------
 constexpr int kMergeSplit = 8;       // CTAs per rank
@@ -1022,9 +1180,13 @@ cudaError_t launch_cfar(const PlanDev &p, const float *pmap, uint32_t *mask, flo
     return cudaGetLastError();
 }
 
-bool is_record_kernel(const void *func)
+int record_kernel_args(const void *func)
 {
-    return func == (const void *)measure_kernel || func == (const void *)measure_wide_kernel;
+    if (func == (const void *)measure_kernel || func == (const void *)measure_wide_kernel) return 12;
+    if (func == (const void *)angle_fft_kernel<64, 8, 8> || func == (const void *)angle_fft_kernel<128, 8, 16> ||
+        func == (const void *)angle_fft_kernel<256, 16, 16>)
+        return 10;
+    return 0;
 }
 
 cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames, int dense_cap, int sm_count, cudaStream_t st)
@@ -1043,6 +1205,22 @@ cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const bool wide = p.A >= kMeasWideA;
+    // wide arrays, fused mode: one more Doppler FFT of the rows that have hits, then the angle spectra as FFTs
+    // (PlanDev.k4_variant = 1 keeps the per-detection kernel below: tests and profiles compare the two)
+    if (wide && !p.keep_cube && b.rows != nullptr && b.snap != nullptr && p.k4_variant != 1) {
+        const int rgrid = (dense_cap + 255) / 256 < sm_count * 4 ? (dense_cap + 255) / 256 : sm_count * 4;
+        rows_kernel<<<rgrid < 1 ? 1 : rgrid, 256, 0, st>>>(p, b.keys, b.offsets, b.rows, b.ticket + 2, n_frames, dense_cap);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = launch_doppler_extract(p, b.rs, b.keys, b.offsets, b.rows, b.ticket + 2, b.snap, dense_cap, n_frames * p.Sp, st);
+        if (e != cudaSuccess) return e;
+        switch (p.n_theta) {
+        case 64:  return run_angle_fft<64, 8, 8>(p, b, n_frames, dense_cap, sm_count, st);
+        case 128: return run_angle_fft<128, 8, 16>(p, b, n_frames, dense_cap, sm_count, st);
+        case 256: return run_angle_fft<256, 16, 16>(p, b, n_frames, dense_cap, sm_count, st);
+        default:  return cudaErrorInvalidValue;
+        }
+    }
     const int bytes = p.n_theta * 8 + (wide ? kMeasWideG : kMeasWarps * kMeasG) * p.A * 8;
     static int configured_dev[kMaxDevices][2] = {{0}};
     int *configured = configured_dev[current_device()];

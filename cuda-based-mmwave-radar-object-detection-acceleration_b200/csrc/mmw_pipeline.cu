@@ -434,6 +434,200 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
 }
 
 // ---------------------------------------------------------------------------
+// K2x: selective Doppler re-FFT (fused mode, wide arrays): antenna snapshots of the detected cells
+// ---------------------------------------------------------------------------
+// In fused mode the Doppler cube is never written, so the angle stage has to re-derive, for every detection (f, r, d), the
+// Doppler bin d of all A antennas at range bin r.  A direct DFT per detection costs A * C complex MACs and a pass over the
+// A x C block of the range spectrum; on the imaging cube (A = 192, C = 512: 786 KB per range bin) with thousands of hits
+// that was the longest stage of the chain.  Here every (frame, range bin) that has at least one hit — `rows`, made by
+// rows_kernel from the ordered key list — is transformed ONCE more with the very FFT K2 runs (same code, same roundings:
+// the snapshot is bit-identical to what the Doppler cube would hold), and only the detected bins are written out, to
+// snap[dense index][antenna].  Cost: one K2 step per hit row, whatever the number of hits in it — bounded by one K2 pass.
+// A tile is BT arbitrary hit rows (each row is its own bulk copy, so they need not be neighbours); staging, the in-place
+// two-pass FFT and the three-stage ring are doppler_fft_kernel's.
+template <int N, int BT>
+struct ExtractSmem {
+    static constexpr int kStageRow = N + 2;
+    static constexpr int kNStage = 3;
+    static constexpr int kOffRows = 32;                              // three mbarriers in front
+    static constexpr int kOffTw = kOffRows + BT * 16 + (BT + 1) * 4 + 12;   // uint4 row refs + prefix counts (padded to 16)
+    static constexpr int kOffStage = ((kOffTw + 8 * N) + 15) / 16 * 16;
+    static constexpr int kBytes = kOffStage + kNStage * BT * kStageRow * 8;
+};
+
+template <int N, int R1, int R2, int BT, int NW, bool PAD>
+__global__ void __launch_bounds__(NW * 32, (2 * ExtractSmem<N, BT>::kBytes <= 226 * 1024 && NW <= 8) ? 2 : 1)
+    doppler_extract_kernel(PlanDev p, const float2 *__restrict__ rs, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ offsets,
+                           const uint4 *__restrict__ rows, const unsigned int *__restrict__ n_rows_ptr, float2 *__restrict__ snap, int dense_cap)
+{
+    static_assert(R1 * R2 == N, "plan");
+    using L = ExtractSmem<N, BT>;
+    constexpr int NT = NW * 32;
+    constexpr int NSTAGE = L::kNStage, AHEAD = NSTAGE - 1;
+    constexpr int SUBS = 32 / BT;
+    constexpr int NSLOT = NW * SUBS;
+    constexpr int LR1 = ilog2(R1), LR2 = ilog2(R2);
+    constexpr int UPS2 = (R1 + NSLOT - 1) / NSLOT;
+    constexpr int UPS1 = (R2 + NSLOT - 1) / NSLOT;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    uint4 *s_row = reinterpret_cast<uint4 *>(smem + L::kOffRows);     // {frame, range bin, dense index of the first hit, hits} per tile row
+    uint32_t *s_pref = reinterpret_cast<uint32_t *>(smem + L::kOffRows + BT * 16);   // [BT + 1] exclusive prefix of the hit counts
+    float2 *tw = reinterpret_cast<float2 *>(smem + L::kOffTw);
+    float2 *stage = reinterpret_cast<float2 *>(smem + L::kOffStage);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = lane % BT, sub = lane / BT, slot = warp * SUBS + sub;
+    const int C = PAD ? p.C : N, A = p.A;
+    const int Sp = p.Sp;
+    const uint32_t n_rows = *n_rows_ptr;
+    const int n_tiles = (int)((n_rows + BT - 1) / BT);
+    if (n_tiles == 0) return;
+    // Antennas are independent here (nothing is accumulated across them), so a tile's antennas are cut into chunks and a
+    // work item is (tile, chunk): a handful of hit rows — a sparse scene — still spreads over every CTA instead of walking
+    // A antennas one after the other inside a few.  Aim: ~8 items per CTA, chunks of at least 4 antennas.
+    int n_chunks = (int)((8LL * gridDim.x + n_tiles - 1) / n_tiles);
+    n_chunks = max(1, min(n_chunks, (A + 3) / 4));
+    const int AC = (A + n_chunks - 1) / n_chunks;                     // antennas per chunk (the last one may be shorter)
+    n_chunks = (A + AC - 1) / AC;
+    const long long n_items = (long long)n_tiles * n_chunks;
+    if ((long long)blockIdx.x >= n_items) return;
+    auto item_antennas = [&](long long item) { const int ch = (int)(item % n_chunks); return min(AC, A - ch * AC); };
+
+    // issue side (warp 0): the staging copies run AHEAD steps in front of the transform, across item boundaries
+    long long is_item = blockIdx.x;
+    int is_a = 0;
+    auto issue_next = [&](int q) {                                    // warp 0: stage the next step in line into buffer q % NSTAGE
+        if (is_item >= n_items) return;
+        const int tile = (int)(is_item / n_chunks), a = (int)(is_item % n_chunks) * AC + is_a;
+        const uint32_t ri = (uint32_t)tile * BT + lane;
+        const bool live = lane < BT && ri < n_rows;
+        const uint32_t nlive = min((uint32_t)BT, n_rows - (uint32_t)tile * BT);
+        const int buf = q % NSTAGE;
+        uint64_t *b = &bar[buf];
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(b, nlive * (uint32_t)(C * 8));
+        }
+        __syncwarp();
+        if (live) {
+            const uint4 rr = rows[ri];
+            const float2 *src = rs + (((size_t)rr.x * A + a) * Sp + rr.y) * (size_t)C;
+            bulk_g2s(stage + (size_t)buf * (BT * L::kStageRow) + lane * L::kStageRow, src, (uint32_t)(C * 8), b);
+        }
+        if (++is_a >= item_antennas(is_item)) { is_a = 0; is_item += gridDim.x; }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(&bar[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < AHEAD; ++i) issue_next(i);
+    }
+    for (int i = tid; i < N; i += NT) tw[i] = p.tw1_d[i];
+
+    int s = 0;
+    int cur_tile = -1;
+    uint32_t H = 0;
+#pragma unroll 1
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = (int)(item / n_chunks), a0 = (int)(item % n_chunks) * AC, na = item_antennas(item);
+        if (tile != cur_tile) {
+            // ---- the tile's rows: where their hits sit in the dense list and how many there are ----
+            __syncthreads();                                          // s_row / s_pref of the previous tile are no longer read
+            for (int i = warp; i < BT; i += NW) {
+                const uint32_t ri = (uint32_t)tile * BT + i;
+                uint4 rr = make_uint4(0u, 0u, 0u, 0u);
+                if (ri < n_rows) {
+                    rr = rows[ri];
+                    const uint32_t fbeg = offsets[rr.x], fend = min(offsets[rr.x + 1], (uint32_t)dense_cap);
+                    const uint32_t *kf = keys + (size_t)rr.x * p.max_det - fbeg;     // kf[g] = key of dense position g
+                    uint32_t n = 0;
+                    for (uint32_t g = rr.z;; g += 32) {               // the run of equal range bin that starts at rr.z
+                        const bool same = g + lane < fend && (kf[g + lane] >> 16) == rr.y;
+                        const uint32_t m = __ballot_sync(0xffffffffu, same);
+                        const uint32_t k = m == 0xffffffffu ? 32u : (uint32_t)(__ffs(~m) - 1);
+                        n += k;
+                        if (k < 32u) break;
+                    }
+                    rr.w = n;
+                }
+                if (lane == 0) s_row[i] = rr;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t acc = 0;
+                for (int i = 0; i < BT; ++i) { s_pref[i] = acc; acc += s_row[i].w; }
+                s_pref[BT] = acc;
+            }
+            __syncthreads();
+            H = s_pref[BT];
+            cur_tile = tile;
+        }
+
+#pragma unroll 1
+        for (int a = a0; a < a0 + na; ++a, ++s) {
+            if (warp == 0) issue_next(s + AHEAD);
+            mbar_wait(&bar[s % NSTAGE], (uint32_t)((s / NSTAGE) & 1));
+            float2 *sbuf = stage + (size_t)(s % NSTAGE) * (BT * L::kStageRow);
+            float2 *srow = sbuf + row * L::kStageRow;
+
+            // pass 1, in place (as doppler_fft_kernel<.., INPLACE>)
+#pragma unroll
+            for (int ui = 0; ui < UPS1; ++ui) {
+                const int n2 = slot + ui * NSLOT;
+                if (UPS1 * NSLOT == R2 || n2 < R2) {
+                    float2 x[R1];
+#pragma unroll
+                    for (int m = 0; m < R1; ++m) {
+                        const int n = n2 + m * R2;
+                        x[m] = (!PAD || n < C) ? srow[n] : make_float2(0.f, 0.f);
+                    }
+                    dft_regs<R1>(x);
+                    float2 *wo = srow + n2;
+                    wo[0] = x[0];
+#pragma unroll
+                    for (int k1 = 1; k1 < R1; ++k1) wo[k1 * R2] = cmul(x[bitrev(k1, LR1)], tw[tw1_index(n2, k1, R1)]);
+                }
+            }
+            __syncthreads();
+            // pass 2; bin k1 + R1 * k2 goes back to srow[k1 * R2 + k2] (the run this thread has just read)
+#pragma unroll
+            for (int ui = 0; ui < UPS2; ++ui) {
+                const int k1 = slot + ui * NSLOT;
+                if (k1 < R1) {
+                    float2 y[R2];
+                    float2 *wi = srow + k1 * R2;
+#pragma unroll
+                    for (int n2 = 0; n2 < R2; ++n2) y[n2] = wi[n2];
+                    dft_regs<R2>(y);
+#pragma unroll
+                    for (int k2 = 0; k2 < R2; ++k2) wi[k2] = y[bitrev(k2, LR2)];
+                }
+            }
+            __syncthreads();
+            // the detected bins of this antenna -> snap[dense index][a]
+            for (uint32_t h = tid; h < H; h += NT) {
+                int i = 0;
+#pragma unroll
+                for (int j = 1; j < BT; ++j) i += (h >= s_pref[j]) ? 1 : 0;
+                const uint4 rr = s_row[i];
+                const uint32_t g = rr.z + (h - s_pref[i]);
+                const uint32_t d = keys[(size_t)rr.x * p.max_det + (g - offsets[rr.x])] & 0xffffu;
+                const float2 v = sbuf[i * L::kStageRow + (d % R1) * R2 + d / R1];
+                st_global_f2(snap + (size_t)g * A + a, v);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K2w: Doppler FFT with warp-private tiles (fused mode: power map only)
 // ---------------------------------------------------------------------------
 // doppler_fft_kernel above shares a 16-row tile between the warps of a CTA, so the two passes are separated by CTA-wide
@@ -848,6 +1042,43 @@ cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube,
     // 16-row double-buffered shape (201 KB, one CTA per SM) on the cfg4 cube (profiles/experiments/r1_cfg4_tile_sweep.log)
     case 512:  return run_doppler<512, 16, 32, 8, 8, 1024, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
     case 1024: return run_doppler<1024, 32, 32, 8, 8, 0, 0>(p, rs, cube, pmap, n_frames, st);
+    default:   return cudaErrorInvalidValue;
+    }
+}
+
+template <int N, int R1, int R2, int BT, int NW>
+static cudaError_t run_extract(const PlanDev &p, const float2 *rs, const uint32_t *keys, const uint32_t *offsets, const uint4 *rows,
+                               const unsigned int *n_rows, float2 *snap, int dense_cap, int max_rows, cudaStream_t st)
+{
+    constexpr int bytes = ExtractSmem<N, BT>::kBytes;
+    const bool pad = p.C != N;
+    auto k = pad ? doppler_extract_kernel<N, R1, R2, BT, NW, true> : doppler_extract_kernel<N, R1, R2, BT, NW, false>;
+    static int per_sm_dev[kMaxDevices][2] = {{0}};
+    int &per_sm = per_sm_dev[current_device()][pad ? 1 : 0];
+    if (!per_sm) {
+        cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    }
+    // the number of hit rows is only known on the device: a persistent grid of every resident CTA, capped by the most work
+    // items there can be (a tile's antennas are split into chunks of >= 4 inside the kernel); idle CTAs leave at once
+    const long long items_max = (((long long)max_rows + BT - 1) / BT) * ((p.A + 3) / 4);
+    const long long resident = (long long)per_sm * sm_count();
+    const int grid = (int)(items_max < resident ? (items_max < 1 ? 1 : items_max) : resident);
+    k<<<grid, NW * 32, bytes, st>>>(p, rs, keys, offsets, rows, n_rows, snap, dense_cap);
+    return cudaGetLastError();
+}
+
+// max_rows: upper bound of the hit rows (n_frames * Sp); the true count is read from *n_rows on the device
+cudaError_t launch_doppler_extract(const PlanDev &p, const float2 *rs, const uint32_t *keys, const uint32_t *offsets, const uint4 *rows,
+                                   const unsigned int *n_rows, float2 *snap, int dense_cap, int max_rows, cudaStream_t st)
+{
+    switch (p.Cp) {
+    case 64:   return run_extract<64, 8, 8, 8, 4>(p, rs, keys, offsets, rows, n_rows, snap, dense_cap, max_rows, st);
+    case 128:  return run_extract<128, 8, 16, 8, 4>(p, rs, keys, offsets, rows, n_rows, snap, dense_cap, max_rows, st);
+    case 256:  return run_extract<256, 16, 16, 8, 8>(p, rs, keys, offsets, rows, n_rows, snap, dense_cap, max_rows, st);
+    case 512:  return run_extract<512, 16, 32, 8, 8>(p, rs, keys, offsets, rows, n_rows, snap, dense_cap, max_rows, st);
+    case 1024: return run_extract<1024, 32, 32, 8, 8>(p, rs, keys, offsets, rows, n_rows, snap, dense_cap, max_rows, st);
     default:   return cudaErrorInvalidValue;
     }
 }

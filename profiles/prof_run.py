@@ -1,4 +1,5 @@
-"""Small fixed run for ncu: 2 batches of the cfg3 shape (8 frames) through the device-resident path."""
+"""Small fixed run for ncu: 3 batches of a bench workload through the device-resident path.
+    python profiles/prof_run.py [cfg3|cfg2|cfg4|cfg5] [scene cfg number, default: the bench's]"""
 import os
 import sys
 
@@ -10,11 +11,13 @@ import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
-S, C, A, F = {"cfg3": (512, 256, 12, 64), "cfg2": (256, 128, 4, 1024)}[wl]
+S, C, A, F, scene, cap = {"cfg3": (512, 256, 12, 64, 3, 4096), "cfg2": (256, 128, 4, 1024, 2, 4096), "cfg4": (1024, 512, 192, 4, 4, 32768),
+                          "cfg5": (256, 128, 12, 64, 5, 4096)}[wl]
+scene = int(sys.argv[2]) if len(sys.argv) > 2 else scene
 dev = torch.device("cuda", 0)
-adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=3)
+adc = pkg.synth.cube_batch_torch(F, S, C, A, dev, cfg=scene)
 torch.cuda.synchronize()
-with pkg.RadarContext(S, C, A, F) as ctx:
+with pkg.RadarContext(S, C, A, F, max_det_per_frame=cap) as ctx:
     for _ in range(3):
         ctx.process_device(adc, F)
     dets, ov = ctx.read_detections()

@@ -171,6 +171,36 @@ def test_cfar_kernel_forms_agree_with_oracle(pkg, orc, cases, variant, monkeypat
     assert hit >= len(dets) - int(near.sum())
 
 
+def test_wide_array_paths_agree(pkg, orc, monkeypatch):
+    """A >= 32 in fused mode: the selective Doppler re-FFT + angle FFT path (default) against the per-detection kernel it
+    replaces (MMW_K4_VARIANT=1 at context creation: direct Doppler DFT + angle DFT per detection) and against cube mode:
+    same cells, powers, noise and flags bit for bit; angle bins identical away from ties of the angle spectrum."""
+    S, C, A, F = 128, 64, 96, 3
+    adc = pkg.synth.cube_batch(F, S, C, A, cfg=13, n_targets=6)
+    wr, wd = orc.hann_periodic(S), orc.hann_periodic(C)
+    ref = orc.process_frames(adc, F, S, C, A, wr, wd, want=("ratio",), n_threads=3)
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        new, ov = ctx.process_host(adc, F)
+        assert not ov and ctx.info.kernels_per_batch == 7
+    monkeypatch.setenv("MMW_K4_VARIANT", "1")
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        old, _ = ctx.process_host(adc, F)
+        assert ctx.info.kernels_per_batch == 5
+    monkeypatch.delenv("MMW_K4_VARIANT")
+    with pkg.RadarContext(S, C, A, F, keep_doppler_cube=True) as ctx:
+        cube, _ = ctx.process_host(adc, F)
+    key = lambda d: (d["frame"].astype(np.int64) << 32) | (d["range_bin"].astype(np.int64) << 16) | d["doppler_bin"]
+    rk = key(ref["dets"])
+    for other, name in ((old, "per-detection kernel"), (cube, "cube mode")):
+        assert len(new) == len(other) > 50, name
+        for fld in ("frame", "range_bin", "doppler_bin", "power", "noise", "flags"):
+            assert np.array_equal(new[fld], other[fld]), (name, fld)
+        _, ni, ri = np.intersect1d(key(new), rk, return_indices=True)
+        clear = ref["ratio"][ri] < 1 - 1e-4
+        assert np.array_equal(new["angle_bin"][ni][clear], other["angle_bin"][ni][clear]), name
+        assert np.array_equal(new["angle_bin"][ni][clear], ref["dets"]["angle_bin"][ri][clear]), name
+
+
 def test_detection_list_overflow_is_ordered_and_counted(pkg, orc):
     S, C, A, F = 64, 64, 2, 3
     rng = np.random.default_rng(5)
