@@ -43,6 +43,8 @@ C_ABI_SYMBOLS = [
     "mmw_legacy_process_frame", "mmw_legacy_process_frames", "mmw_legacy_copy_spectrum", "mmw_legacy_shutdown",
     "mmw_legacy_process_device", "mmw_legacy_sync", "mmw_legacy_distance_from_raw", "mmw_legacy_process_file",
     "mmw_legacy_configure",
+    "mmw_group_create", "mmw_group_destroy", "mmw_group_size", "mmw_group_context", "mmw_group_set_frame_offset", "mmw_shard_frames",
+    "mmw_group_process_host", "mmw_group_process_device", "mmw_group_merged_block", "mmw_group_read_detections",
 ]
 # the reference's own entry point (acceleration.h:32), C++ linkage
 LEGACY_MANGLED = "_Z14cudaProcessingPsP9Complex_tiPdS2_S2_S2_"
@@ -140,6 +142,19 @@ def load(build_if_missing: bool = True):
     L.mmw_legacy_process_frames.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
     L.mmw_legacy_copy_spectrum.argtypes = [vp]
     L.mmw_legacy_shutdown.restype = None
+    L.mmw_group_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.mmw_group_destroy.argtypes = [vp]
+    L.mmw_group_destroy.restype = None
+    L.mmw_group_size.argtypes = [vp]
+    L.mmw_group_context.argtypes = [vp, C.c_int]
+    L.mmw_group_context.restype = vp
+    L.mmw_group_set_frame_offset.argtypes = [vp, C.c_uint32]
+    L.mmw_shard_frames.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
+    L.mmw_shard_frames.restype = None
+    L.mmw_group_process_host.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip]
+    L.mmw_group_process_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int)]
+    L.mmw_group_merged_block.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
+    L.mmw_group_read_detections.argtypes = [vp, vp, C.c_int, ip]
     L.mmw_legacy_configure.argtypes = [C.c_int, C.c_int]
     cp = getattr(L, LEGACY_MANGLED)
     cp.restype = C.c_double
@@ -372,6 +387,91 @@ class RadarContext:
         _check(self._L.mmw_time_device(self._h, C.c_void_p(_dev_ptr(adc_dev)), n_frames, iters, C.byref(total),
                                        stages if per_stage else None))
         return (total.value, list(stages)) if per_stage else total.value
+
+
+class RadarGroup:
+    """A frame-sharded group of GPUs driven by this process (mmw_group_*): one context per device, one NCCL communicator,
+    detection lists gathered to the first device.  max_frames is the capacity PER GPU."""
+
+    def __init__(self, n_samples: int, n_chirps: int, n_antennas: int, max_frames: int, devices, **kw):
+        self._L = load()
+        cfg = Config()
+        self._L.mmw_default_config(C.byref(cfg), n_samples, n_chirps, n_antennas, max_frames)
+        cfg.cfar_guard_r, cfg.cfar_guard_d = kw.get("cfar_guard", (2, 2))
+        cfg.cfar_train_r, cfg.cfar_train_d = kw.get("cfar_train", (8, 4))
+        cfg.cfar_alpha = kw.get("cfar_alpha", 15.0)
+        cfg.max_det_per_frame = kw.get("max_det_per_frame", 1024)
+        cfg.keep_doppler_cube = int(kw.get("keep_doppler_cube", False))
+        cfg.lambda_over_d = kw.get("lambda_over_d", 2.0)
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        _check(self._L.mmw_group_create(C.byref(cfg), devs, len(devices), C.byref(self._h)))
+        self.devices = list(devices)
+        self.max_frames, self.max_det_per_frame = max_frames, cfg.max_det_per_frame
+        self.frame_shorts = 2 * n_samples * n_chirps * n_antennas
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.mmw_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def size(self) -> int:
+        return self._L.mmw_group_size(self._h)
+
+    def set_frame_offset(self, first_frame: int):
+        _check(self._L.mmw_group_set_frame_offset(self._h, int(first_frame)))
+
+    def process_host(self, adc_host, n_frames: int, det_capacity: int | None = None):
+        """Host capture -> shards -> chain on every GPU -> NCCL gather to device 0 -> (detections, overflow_flag)."""
+        if isinstance(adc_host, np.ndarray):
+            a = np.ascontiguousarray(adc_host, np.int16)
+            ptr, n = a.ctypes.data, a.size
+        else:
+            ptr, n = adc_host.data_ptr(), adc_host.numel()
+        if n < n_frames * self.frame_shorts:
+            raise ValueError("capture buffer shorter than n_frames frames")
+        cap = det_capacity if det_capacity is not None else n_frames * self.max_det_per_frame
+        dets = np.empty(cap, DET_DTYPE)
+        n_det = C.c_int(0)
+        rc = _check(self._L.mmw_group_process_host(self._h, C.c_void_p(ptr), n_frames, _np_ptr(dets), cap, C.byref(n_det)), True)
+        return dets[: n_det.value], rc == MMW_ERR_OVERFLOW
+
+    def process_device(self, shards, n_frames):
+        """shards[i]: torch int16 CUDA tensor on the group's i-th device (or None / an address) holding n_frames[i] frames."""
+        ptrs = (C.c_void_p * len(shards))(*[C.c_void_p(_dev_ptr(t) if t is not None else 0) for t in shards])
+        cnt = (C.c_int * len(shards))(*[int(v) for v in n_frames])
+        _check(self._L.mmw_group_process_device(self._h, ptrs, cnt))
+
+    def read_detections(self, det_capacity: int | None = None):
+        cap = det_capacity if det_capacity is not None else self.size * self.max_frames * self.max_det_per_frame
+        dets = np.empty(cap, DET_DTYPE)
+        n_det = C.c_int(0)
+        rc = _check(self._L.mmw_group_read_detections(self._h, _np_ptr(dets), cap, C.byref(n_det)), True)
+        return dets[: n_det.value].copy(), rc == MMW_ERR_OVERFLOW
+
+    def merged_block(self):
+        b, n = C.c_void_p(), C.c_longlong(0)
+        _check(self._L.mmw_group_merged_block(self._h, C.byref(b), C.byref(n)))
+        return int(b.value), int(n.value)
+
+
+def shard_frames(n_frames: int, n_ranks: int, rank: int):
+    first, count = C.c_int(0), C.c_int(0)
+    load().mmw_shard_frames(n_frames, n_ranks, rank, C.byref(first), C.byref(count))
+    return first.value, count.value
 
 
 def default_radar_params() -> RadarParams:

@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-Xptxas", "-v" if verbose else "-O3",
         "-shared", "-Xcompiler", "-fPIC",
         "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+    ] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]      # dlopen of libnccl.so.2 (mmw_group_create); NCCL itself is not linked
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

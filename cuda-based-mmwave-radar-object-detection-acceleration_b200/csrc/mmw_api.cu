@@ -2,7 +2,9 @@
 // HBM workspace, stream, and the launch sequence of one batch.  No torch types, no CPU compute
 // path: every processing call either launches the CUDA kernels or fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>       // types and prototypes only: the functions are resolved from libnccl.so.2 at run time (mmw_group_create)
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -936,6 +938,302 @@ int mmw_time_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames, int iters,
     CK(cudaEventSynchronize(c->ev[5]));
     CK(cudaEventElapsedTime(total_ms, c->ev[0], c->ev[5]));
     return MMW_OK;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU group: frame shards on the GPUs of one process, detection lists gathered to GPU 0 over NCCL
+// ---------------------------------------------------------------------------
+struct NcclApi {
+    void *handle;
+    decltype(&ncclGetUniqueId) GetUniqueId;
+    decltype(&ncclCommInitRankConfig) CommInitRankConfig;
+    decltype(&ncclCommInitAll) CommInitAll;
+    decltype(&ncclCommDestroy) CommDestroy;
+    decltype(&ncclGroupStart) GroupStart;
+    decltype(&ncclGroupEnd) GroupEnd;
+    decltype(&ncclSend) Send;
+    decltype(&ncclRecv) Recv;
+    decltype(&ncclGetErrorString) GetErrorString;
+};
+
+struct mmw_group {
+    int n;
+    std::vector<mmw_ctx *> ctx;
+    std::vector<int> dev;
+    std::vector<ncclComm_t> comm;
+    NcclApi nccl;
+    unsigned char *d_merged;          // on dev[0]: [32-byte header | records of all ranks, ordered]
+    long long merged_cap;             // records d_merged can hold
+    uint32_t *h_headers;              // pinned: 8 words per rank
+    uint32_t *h_merged_header;        // pinned: 8 words
+    uint32_t frame_offset;
+    int gathered;                     // a merged block is queued / ready on GPU 0
+};
+
+#define NCCLCK(g, call)                                                                                   \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) {                                                                          \
+            set_last_error("%s failed: %s", #call, (g)->nccl.GetErrorString ? (g)->nccl.GetErrorString(r_) : "?"); \
+            return MMW_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static int load_nccl(NcclApi *api)
+{
+    memset(api, 0, sizeof(*api));
+    // the soname torch's bundled NCCL and the system NCCL share: if one is already in the process, this is it
+    api->handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api->handle) { set_last_error("mmw_group_create: cannot load libnccl.so.2 (%s)", dlerror()); return MMW_ERR_STATE; }
+#define NCCL_SYM(field, name) api->field = reinterpret_cast<decltype(api->field)>(dlsym(api->handle, name))
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    NCCL_SYM(CommInitRankConfig, "ncclCommInitRankConfig");
+    NCCL_SYM(CommInitAll, "ncclCommInitAll");
+    NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    NCCL_SYM(GroupStart, "ncclGroupStart");
+    NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    NCCL_SYM(Send, "ncclSend");
+    NCCL_SYM(Recv, "ncclRecv");
+    NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+    if (!api->CommInitAll || !api->CommDestroy || !api->GroupStart || !api->GroupEnd || !api->Send || !api->Recv) {
+        set_last_error("mmw_group_create: libnccl.so.2 lacks a required symbol");
+        return MMW_ERR_STATE;
+    }
+    return MMW_OK;
+}
+
+void mmw_shard_frames(int n_frames, int n_ranks, int rank, int *first, int *count)
+{
+    if (n_ranks < 1) n_ranks = 1;
+    const int base = n_frames / n_ranks, rem = n_frames % n_ranks;
+    if (count) *count = base + (rank < rem ? 1 : 0);
+    if (first) *first = rank * base + (rank < rem ? rank : rem);
+}
+
+void mmw_group_destroy(mmw_group *g)
+{
+    if (!g) return;
+    for (size_t i = 0; i < g->comm.size(); ++i)
+        if (g->comm[i] && g->nccl.CommDestroy) {
+            cudaSetDevice(g->dev[i]);
+            g->nccl.CommDestroy(g->comm[i]);
+        }
+    if (!g->dev.empty()) cudaSetDevice(g->dev[0]);
+    if (g->d_merged) cudaFree(g->d_merged);
+    if (g->h_headers) cudaFreeHost(g->h_headers);
+    if (g->h_merged_header) cudaFreeHost(g->h_merged_header);
+    for (mmw_ctx *c : g->ctx) mmw_destroy(c);
+    delete g;
+}
+
+int mmw_group_create(const mmw_config *cfg, const int *devices, int n_devices, mmw_group **out)
+{
+    if (!cfg || !devices || !out || n_devices < 1 || n_devices > kMaxDevices) { set_last_error("mmw_group_create: bad argument"); return MMW_ERR_ARG; }
+    *out = nullptr;
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) { set_last_error("mmw_group_create: device %d listed twice", devices[i]); return MMW_ERR_ARG; }
+    mmw_group *g = new mmw_group();
+    g->n = n_devices;
+    g->d_merged = nullptr; g->h_headers = nullptr; g->h_merged_header = nullptr; g->frame_offset = 0; g->gathered = 0; g->merged_cap = 0;
+    memset(&g->nccl, 0, sizeof(g->nccl));
+    auto fail = [&](int code) { mmw_group_destroy(g); return code; };
+    for (int i = 0; i < n_devices; ++i) {
+        mmw_config c = *cfg;
+        c.device = devices[i];
+        mmw_ctx *ctx = nullptr;
+        const int rc = mmw_create(&c, &ctx);
+        if (rc) return fail(rc);
+        g->ctx.push_back(ctx);
+        g->dev.push_back(ctx->device);
+        g->merged_cap += ctx->dense_cap;
+    }
+    if (cudaSetDevice(g->dev[0]) != cudaSuccess ||
+        cudaMalloc((void **)&g->d_merged, kResultHeaderBytes + (size_t)g->merged_cap * sizeof(mmw_detection)) != cudaSuccess ||
+        cudaMallocHost((void **)&g->h_headers, (size_t)n_devices * 32) != cudaSuccess ||
+        cudaMallocHost((void **)&g->h_merged_header, 32) != cudaSuccess) {
+        set_last_error("mmw_group_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(MMW_ERR_CUDA);
+    }
+    if (n_devices > 1) {
+        int rc = load_nccl(&g->nccl);
+        if (rc) return fail(rc);
+        g->comm.assign(n_devices, nullptr);
+        if (g->nccl.CommInitRankConfig && g->nccl.GetUniqueId) {
+            // one CTA per peer: the gather moves KBs, and a wider NCCL kernel would evict the persistent CTAs of the FFT kernels
+            ncclConfig_t conf = NCCL_CONFIG_INITIALIZER;
+            conf.minCTAs = 1;
+            conf.maxCTAs = 1;
+            ncclUniqueId id;
+            ncclResult_t r = g->nccl.GetUniqueId(&id);
+            if (r == ncclSuccess) r = g->nccl.GroupStart();
+            for (int i = 0; r == ncclSuccess && i < n_devices; ++i) {
+                cudaSetDevice(g->dev[i]);
+                r = g->nccl.CommInitRankConfig(&g->comm[i], n_devices, id, i, &conf);
+            }
+            if (r == ncclSuccess) r = g->nccl.GroupEnd();
+            if (r != ncclSuccess) {
+                set_last_error("mmw_group_create: NCCL communicator init failed: %s", g->nccl.GetErrorString ? g->nccl.GetErrorString(r) : "?");
+                return fail(MMW_ERR_CUDA);
+            }
+        } else {
+            const ncclResult_t r = g->nccl.CommInitAll(g->comm.data(), n_devices, g->dev.data());
+            if (r != ncclSuccess) {
+                set_last_error("mmw_group_create: ncclCommInitAll failed: %s", g->nccl.GetErrorString ? g->nccl.GetErrorString(r) : "?");
+                return fail(MMW_ERR_CUDA);
+            }
+        }
+    }
+    *out = g;
+    return MMW_OK;
+}
+
+int mmw_group_size(const mmw_group *g) { return g ? g->n : 0; }
+
+mmw_ctx *mmw_group_context(mmw_group *g, int i) { return (g && i >= 0 && i < g->n) ? g->ctx[i] : nullptr; }
+
+int mmw_group_set_frame_offset(mmw_group *g, uint32_t first_frame)
+{
+    if (!g) { set_last_error("mmw_group_set_frame_offset: null group"); return MMW_ERR_ARG; }
+    g->frame_offset = first_frame;
+    return MMW_OK;
+}
+
+// the exchange step: headers to the host, then exactly count_r records from every rank to their final offsets on GPU 0
+static int group_gather(mmw_group *g, const int *n_frames)
+{
+    const int n = g->n;
+    for (int i = 0; i < n; ++i) {
+        mmw_ctx *c = g->ctx[i];
+        CK(cudaSetDevice(c->device));
+        if (n_frames[i] > 0)
+            CK(cudaMemcpyAsync(g->h_headers + 8 * i, c->d_header, 32, cudaMemcpyDeviceToHost, c->stream));
+        else
+            memset(g->h_headers + 8 * i, 0, 32);
+    }
+    for (int i = 0; i < n; ++i) {
+        CK(cudaSetDevice(g->ctx[i]->device));
+        CK(cudaStreamSynchronize(g->ctx[i]->stream));
+    }
+    uint64_t off = 0, true_total = 0, frames = 0;
+    uint32_t overflow = 0;
+    std::vector<uint64_t> offs(n), cnt(n);
+    for (int i = 0; i < n; ++i) {
+        const uint32_t *h = g->h_headers + 8 * i;
+        offs[i] = off;
+        cnt[i] = h[0];
+        if (off + cnt[i] > (uint64_t)g->merged_cap) { cnt[i] = (uint64_t)g->merged_cap > off ? (uint64_t)g->merged_cap - off : 0; overflow = 1; }
+        off += cnt[i];
+        true_total += h[1];
+        frames += h[2];
+        overflow |= h[3];
+    }
+    mmw_ctx *c0 = g->ctx[0];
+    unsigned char *rec0 = g->d_merged + kResultHeaderBytes;
+    CK(cudaSetDevice(c0->device));
+    if (cnt[0] > 0)
+        CK(cudaMemcpyAsync(rec0, c0->d_dense, cnt[0] * sizeof(mmw_detection), cudaMemcpyDeviceToDevice, c0->stream));
+    bool any = false;
+    for (int r = 1; r < n; ++r) any |= cnt[r] > 0;
+    if (any) {
+        NCCLCK(g, g->nccl.GroupStart());
+        for (int r = 1; r < n; ++r) {
+            if (cnt[r] == 0) continue;
+            const size_t bytes = (size_t)cnt[r] * sizeof(mmw_detection);
+            CK(cudaSetDevice(g->ctx[r]->device));
+            NCCLCK(g, g->nccl.Send(g->ctx[r]->d_dense, bytes, ncclUint8, 0, g->comm[r], g->ctx[r]->stream));
+            CK(cudaSetDevice(c0->device));
+            NCCLCK(g, g->nccl.Recv(rec0 + offs[r] * sizeof(mmw_detection), bytes, ncclUint8, r, g->comm[0], c0->stream));
+        }
+        NCCLCK(g, g->nccl.GroupEnd());
+    }
+    uint32_t *mh = g->h_merged_header;
+    memset(mh, 0, 32);
+    mh[0] = (uint32_t)off;
+    mh[1] = (uint32_t)true_total;
+    mh[2] = (uint32_t)frames;
+    mh[3] = overflow ? 1u : 0u;
+    CK(cudaSetDevice(c0->device));
+    CK(cudaMemcpyAsync(g->d_merged, mh, 32, cudaMemcpyHostToDevice, c0->stream));
+    g->gathered = 1;
+    return MMW_OK;
+}
+
+int mmw_group_process_device(mmw_group *g, const int16_t *const *adc_dev, const int *n_frames)
+{
+    if (!g || !adc_dev || !n_frames) { set_last_error("mmw_group_process_device: null argument"); return MMW_ERR_ARG; }
+    g->gathered = 0;
+    uint32_t first = g->frame_offset;
+    for (int i = 0; i < g->n; ++i) {
+        mmw_ctx *c = g->ctx[i];
+        if (n_frames[i] < 0 || n_frames[i] > c->cfg.max_frames) { set_last_error("mmw_group_process_device: n_frames[%d] = %d outside 0..max_frames", i, n_frames[i]); return MMW_ERR_ARG; }
+        if (n_frames[i] == 0) continue;
+        int rc = check_batch_args(c, adc_dev[i], n_frames[i], "mmw_group_process_device");
+        if (rc) return rc;
+        CK(cudaSetDevice(c->device));
+        if ((rc = check_device_capture(adc_dev[i], "mmw_group_process_device"))) return rc;
+        c->plan.frame_offset = first;
+        if ((rc = run_batch_graphed(c, adc_dev[i], n_frames[i]))) return rc;
+        first += (uint32_t)n_frames[i];
+    }
+    return group_gather(g, n_frames);
+}
+
+int mmw_group_merged_block(mmw_group *g, const void **block_dev0, long long *capacity_bytes)
+{
+    if (!g) { set_last_error("mmw_group_merged_block: null group"); return MMW_ERR_ARG; }
+    if (block_dev0) *block_dev0 = g->d_merged;
+    if (capacity_bytes) *capacity_bytes = kResultHeaderBytes + g->merged_cap * (long long)sizeof(mmw_detection);
+    return MMW_OK;
+}
+
+int mmw_group_read_detections(mmw_group *g, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    if (n_det) *n_det = 0;
+    if (!g) { set_last_error("mmw_group_read_detections: null group"); return MMW_ERR_ARG; }
+    if (!g->gathered) { set_last_error("mmw_group_read_detections: no batch gathered"); return MMW_ERR_STATE; }
+    mmw_ctx *c0 = g->ctx[0];
+    CK(cudaSetDevice(c0->device));
+    CK(cudaStreamSynchronize(c0->stream));
+    uint32_t n = g->h_merged_header[0];
+    int rc = g->h_merged_header[3] ? MMW_ERR_OVERFLOW : MMW_OK;
+    if ((int)n > det_capacity) { n = det_capacity > 0 ? (uint32_t)det_capacity : 0; rc = MMW_ERR_OVERFLOW; }
+    if (n > 0) {
+        if (!dets) { set_last_error("detections pointer is null"); return MMW_ERR_ARG; }
+        CK(cudaMemcpy(dets, g->d_merged + kResultHeaderBytes, (size_t)n * sizeof(mmw_detection), cudaMemcpyDeviceToHost));
+    }
+    if (n_det) *n_det = (int)n;
+    if (rc == MMW_ERR_OVERFLOW) set_last_error("detection list truncated: %u of %u detections kept", n, g->h_merged_header[1]);
+    return rc;
+}
+
+int mmw_group_process_host(mmw_group *g, const int16_t *adc_host, int n_frames, mmw_detection *dets, int det_capacity, int *n_det)
+{
+    if (n_det) *n_det = 0;
+    if (!g || !adc_host) { set_last_error("mmw_group_process_host: null argument"); return MMW_ERR_ARG; }
+    if (n_frames < 1 || n_frames > g->n * g->ctx[0]->cfg.max_frames) {
+        set_last_error("mmw_group_process_host: n_frames %d outside 1..%d (n_devices * max_frames)", n_frames, g->n * g->ctx[0]->cfg.max_frames);
+        return MMW_ERR_ARG;
+    }
+    g->gathered = 0;
+    std::vector<int> cnt(g->n);
+    const size_t frame_shorts = (size_t)2 * g->ctx[0]->plan.S * g->ctx[0]->plan.C * g->ctx[0]->plan.A;
+    // every GPU's upload and chain are queued before any is waited for: the shards run side by side
+    for (int i = 0; i < g->n; ++i) {
+        int first = 0;
+        mmw_shard_frames(n_frames, g->n, i, &first, &cnt[i]);
+        if (cnt[i] == 0) continue;
+        mmw_ctx *c = g->ctx[i];
+        int rc = check_batch_args(c, adc_host, cnt[i], "mmw_group_process_host");
+        if (rc) return rc;
+        CK(cudaSetDevice(c->device));
+        c->plan.frame_offset = g->frame_offset + (uint32_t)first;
+        if ((rc = run_host_batch(c, adc_host + (size_t)first * frame_shorts, cnt[i]))) return rc;
+    }
+    const int rc = group_gather(g, cnt.data());
+    if (rc) return rc;
+    return mmw_group_read_detections(g, dets, det_capacity, n_det);
 }
 
 }  // extern "C"

@@ -162,6 +162,43 @@ int mmw_device_result_block(mmw_ctx *ctx, const void **block, long long *capacit
 int mmw_merge_gathered(mmw_ctx *ctx, const void *gathered_dev, int n_ranks, long long stride_bytes,
                        void *merged_dev, int merged_capacity);
 
+/* ---- multi-GPU: a frame-sharded group of GPUs driven by ONE host process ----
+ * The reference is single-GPU, one frame per call (acceleration.h:32, cudaBenchMarking.cpp:374-378); frames are independent,
+ * so a batch shards by frame.  A group owns one context per device (same config; cfg->max_frames is the capacity PER GPU)
+ * and one NCCL communicator over them (single process, one rank per device; NCCL is loaded at run time from libnccl.so.2,
+ * the library has no link-time dependency on it).  A batch of n frames is cut into contiguous blocks — GPU i gets frames
+ * [first_i, first_i + n_i), remainders to the low ranks — every GPU runs the whole chain on its block with no data-path
+ * collective, and the one exchange step gathers the ordered detection lists to GPU 0: the 32-byte headers first, then
+ * exactly count_i records from each rank (grouped ncclSend / ncclRecv over NVLink), landing at their final offsets of one
+ * merged block [32-byte header | records ordered by (frame, range, doppler)] in GPU 0's memory.  mmw_detection.frame
+ * counts from the start of the batch (plus mmw_group_set_frame_offset).  The NCCL kernels are held to one CTA per peer
+ * (ncclConfig_t.maxCTAs) so that they do not evict the persistent FFT kernels of a batch in flight.
+ * One-process-per-GPU launchers (torchrun) use mmw_device_result_block / mmw_merge_gathered with their own communicator
+ * instead (sharding.py).  Not thread-safe: drive a group from one host thread. */
+typedef struct mmw_group mmw_group;
+int mmw_group_create(const mmw_config *cfg, const int *devices, int n_devices, mmw_group **out);
+void mmw_group_destroy(mmw_group *group);
+int mmw_group_size(const mmw_group *group);
+/* the context on the i-th device of the group (windows, base frame, intermediates of its shard); owned by the group */
+mmw_ctx *mmw_group_context(mmw_group *group, int i);
+/* index of the batch's first frame (added to every record's frame field) */
+int mmw_group_set_frame_offset(mmw_group *group, uint32_t first_frame);
+/* frames [first, first + count) of an n-frame batch owned by rank `rank` of `n_ranks` (the rule the group uses) */
+void mmw_shard_frames(int n_frames, int n_ranks, int rank, int *first, int *count);
+/* Host capture of n_frames frames (n_frames <= n_devices * max_frames; should be pinned) -> sharded upload -> chain on
+ * every GPU -> NCCL gather to GPU 0 -> ordered detection list on the host.  Same result, byte for byte, as one GPU
+ * processing the whole batch.  Returns MMW_OK or MMW_ERR_OVERFLOW as mmw_process_host does. */
+int mmw_group_process_host(mmw_group *group, const int16_t *adc_host, int n_frames,
+                           mmw_detection *dets, int det_capacity, int *n_det);
+/* Device-resident shards: adc_dev[i] points at n_frames[i] frames in the memory of the group's i-th device (n_frames[i]
+ * may be 0).  Runs the chain and the gather; the merged block stays on GPU 0. */
+int mmw_group_process_device(mmw_group *group, const int16_t *const *adc_dev, const int *n_frames);
+/* after mmw_group_process_device: the merged block on GPU 0 ([MMW_RESULT_HEADER_BYTES header | records]); the gather has
+ * been queued on GPU 0's stream (mmw_stream(mmw_group_context(group, 0))) — synchronise that stream before reading */
+int mmw_group_merged_block(mmw_group *group, const void **block_dev0, long long *capacity_bytes);
+/* after mmw_group_process_device: waits for the gather and copies the merged list to the host */
+int mmw_group_read_detections(mmw_group *group, mmw_detection *dets, int det_capacity, int *n_det);
+
 /* ---- capture-file ingest (the caller side of the boundary: the fopen/fread loop of cudaBenchMarking.cpp:339-378) ----
  * Reads a raw capture (frames of 2*S*C*A little-endian int16, no header — the fhy_direct.bin format) from `path`,
  * starting at frame `first_frame`, at most `max_frames` frames (<= 0: to the end of the file), and runs the chain over
