@@ -40,6 +40,7 @@ static int next_pow2(int n)
 using namespace mmw;
 
 constexpr int kMaxChunks = 32;
+constexpr int kFrontStatsCtas = 1024;     // CTAs the optional timing record of the fused front kernel has room for
 constexpr int kResultHeaderBytes = MMW_RESULT_HEADER_BYTES;
 
 struct mmw_ctx {
@@ -67,6 +68,8 @@ struct mmw_ctx {
     uint32_t *d_counts;
     uint32_t *d_offsets;
     unsigned int *d_ticket;
+    unsigned long long *d_front_stats;   // MMW_FRONT_STATS=1 only
+    unsigned int *d_front_sync;   // produced / consumed slab counters of the fused front kernel, [2][max_frames * A]
     uint4 *d_rows;            // hit rows of the selective Doppler re-FFT (wide arrays, fused mode)
     float2 *d_snap;           // antenna snapshots of the detected cells (same path)
     unsigned char *d_result;  // [32-byte header | dense ordered detection list]: one D2H usually moves both
@@ -199,7 +202,7 @@ void mmw_destroy(mmw_ctx *c)
     cudaSetDevice(c->device);
     cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
     cudaFree(c->d_adc); cudaFree(c->d_base); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_psplit); cudaFree(c->d_mask);
-    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_rows); cudaFree(c->d_snap); cudaFree(c->d_result); cudaFree(c->d_scratch);
+    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_front_sync); cudaFree(c->d_front_stats); cudaFree(c->d_rows); cudaFree(c->d_snap); cudaFree(c->d_result); cudaFree(c->d_scratch);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto &h : c->h_ring) if (h) cudaFreeHost(h);
     for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
@@ -278,6 +281,7 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     if ((rc = dev_alloc(c, &c->d_counts, (size_t)F))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_offsets, (size_t)F + 1))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_ticket, (size_t)4))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_front_sync, (size_t)2 * F * A))) return fail(rc);
     if (cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     c->dense_cap = F * cfg->max_det_per_frame;
     // wide arrays without a Doppler cube: snapshots of the detected cells come from a selective re-FFT of the hit rows
@@ -320,6 +324,13 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     // kernel-shape overrides of the sweeps under profiles/ and of the kernel-form parity tests: read once, here
     p.k1_variant = env_int("MMW_K1_VARIANT"); p.k2_variant = env_int("MMW_K2_VARIANT"); p.k3_variant = env_int("MMW_K3_VARIANT");
     p.k4_variant = env_int("MMW_K4_VARIANT"); p.ctas_per_sm_cap = env_int("MMW_CTAS_PER_SM");
+    p.front_variant = env_int("MMW_FRONT"); p.front_window = env_int("MMW_FRONT_WINDOW");
+    p.front_stats = nullptr;
+    if (env_int("MMW_FRONT_STATS")) {
+        if ((rc = dev_alloc(c, &c->d_front_stats, (size_t)kFrontStatsCtas * 8))) return fail(rc);
+        if (cudaMemset(c->d_front_stats, 0, (size_t)kFrontStatsCtas * 8 * sizeof(unsigned long long)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
+        p.front_stats = c->d_front_stats;
+    }
     p.win_r = c->d_win_r; p.win_d = c->d_win_d; p.tw_d = c->d_tw_d; p.tw_a = c->d_tw_a; p.tw1_r = c->d_tw1_r; p.tw1_d = c->d_tw1_d;
 
     // antenna-split Doppler path of small batches (run_front): per-antenna power maps for the largest batch that still
@@ -411,6 +422,13 @@ int mmw_use_stream(mmw_ctx *c, void *cuda_stream)
     return MMW_OK;
 }
 
+static bool front_uses_fused(const PlanDev &p, int n_frames)
+{
+    if (p.front_variant == 1) return false;
+    if (p.front_variant != 2 && p.front_variant != 3) return false;  // default: two kernels (until measured otherwise)
+    return front_fused_supported(p, n_frames);
+}
+
 // stages 1-3 on frames [first, first + n) of the batch (they are per-frame independent)
 static int run_front(mmw_ctx *c, const int16_t *adc_dev, int first, int n, cudaEvent_t *stage_ev)
 {
@@ -421,9 +439,18 @@ static int run_front(mmw_ctx *c, const int16_t *adc_dev, int first, int n, cudaE
     float2 *rs = c->d_rs + (size_t)first * p.A * p.Sp * p.C;
     float2 *cube = p.keep_cube ? c->d_cube + (size_t)first * p.A * M : nullptr;
     if (stage_ev) CK(cudaEventRecord(stage_ev[0], st));
+    const bool split = !cube && n <= c->psplit_frames && doppler_prefers_split(p, n);     // d_psplit: mmw_create
+    if (!split && front_uses_fused(p, n)) {
+        // K1 and K2 as the two roles of one kernel: the Doppler role reads the range spectrum out of the L2 (mmw_front.cuh)
+        CK(launch_front_fused(p, adc, rs, c->d_pmap + (size_t)first * M, n, c->d_front_sync, st));
+        if (stage_ev) CK(cudaEventRecord(stage_ev[1], st));          // (no boundary between the two stages: all of it is booked on stage 1)
+        if (stage_ev) CK(cudaEventRecord(stage_ev[2], st));
+        CK(launch_cfar(p, c->d_pmap + (size_t)first * M, c->d_mask + (size_t)first * (M / 32), c->d_noise + (size_t)first * M, n, c->sm_count, st));
+        if (stage_ev) CK(cudaEventRecord(stage_ev[3], st));
+        return MMW_OK;
+    }
     CK(launch_range_fft(p, adc, rs, n, st));
     if (stage_ev) CK(cudaEventRecord(stage_ev[1], st));
-    const bool split = !cube && n <= c->psplit_frames && doppler_prefers_split(p, n);     // d_psplit: mmw_create
     if (split) {
         PlanDev q = p;                                   // [F][A][Sp][C] read as F*A single-antenna frames
         q.A = 1;
@@ -903,6 +930,17 @@ int mmw_copy_cfar_mask(mmw_ctx *c, int frame, uint8_t *out)
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(out, c->d_scratch, n, cudaMemcpyDeviceToHost));
     return MMW_OK;
+}
+
+int mmw_front_stats(mmw_ctx *c, unsigned long long *out, int max_ctas)
+{
+    if (!c || !out || max_ctas < 1) { set_last_error("mmw_front_stats: bad argument"); return MMW_ERR_ARG; }
+    if (!c->d_front_stats) { set_last_error("mmw_front_stats: the context was created without MMW_FRONT_STATS=1"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int n = max_ctas < kFrontStatsCtas ? max_ctas : kFrontStatsCtas;
+    CK(cudaMemcpy(out, c->d_front_stats, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int mmw_time_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames, int iters, float *total_ms, float *per_stage_ms)

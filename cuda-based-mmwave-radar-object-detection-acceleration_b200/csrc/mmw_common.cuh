@@ -30,6 +30,10 @@ struct PlanDev {
     // host-side only: kernel-shape overrides for the sweeps under profiles/ and the kernel-form parity tests.  Read ONCE, in
     // mmw_create (MMW_K1_VARIANT / MMW_K2_VARIANT / MMW_K3_VARIANT / MMW_K4_VARIANT / MMW_CTAS_PER_SM); 0 = pick by shape.
     int k1_variant, k2_variant, k3_variant, k4_variant, ctas_per_sm_cap;
+    // MMW_FRONT: 0 = pick (fused front where supported), 1 = K1 and K2 as two kernels, 2 = fused front wherever supported;
+    // MMW_FRONT_WINDOW: slabs the producer role may run ahead of the consumer role (0 = derived from the grid)
+    int front_variant, front_window;
+    unsigned long long *front_stats;   // MMW_FRONT_STATS=1: per-CTA timing record of the fused front kernel (mmw_front_stats), else nullptr
 };
 
 // internal HBM layouts
@@ -96,6 +100,10 @@ __device__ __forceinline__ void st_global_f2(float2 *p, float2 v)
 // ---------------------------------------------------------------------------
 cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st);
 cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube, float *pmap, int n_frames, cudaStream_t st);
+// K1 + K2 as one cooperative kernel whose Doppler role reads the range spectrum back out of the L2 (mmw_front.cuh);
+// sync: 2 * n_frames * A counters (zeroed by the launcher)
+bool front_fused_supported(const PlanDev &p, int n_frames);
+cudaError_t launch_front_fused(const PlanDev &p, const int16_t *adc, float2 *rs, float *pmap, int n_frames, unsigned int *sync, cudaStream_t st);
 // small batches: K2 over F*A single-antenna frames into per-antenna maps, then the ordered sum (mmw_pipeline.cu)
 bool doppler_prefers_split(const PlanDev &p, int n_frames);
 cudaError_t launch_power_sum(const PlanDev &p, const float *per_antenna, float *pmap, int n_frames, cudaStream_t st);

@@ -797,6 +797,10 @@ __global__ void __launch_bounds__(256) power_sum_kernel(const float *__restrict_
     }
 }
 
+}  // namespace mmw
+#include "mmw_front.cuh"
+namespace mmw {
+
 // ---------------------------------------------------------------------------
 // export kernels (not on the hot path)
 // ---------------------------------------------------------------------------
@@ -973,6 +977,81 @@ static cudaError_t run_doppler(const PlanDev &p, const float2 *rs, float2 *cube,
         return run_doppler_t<N, R1, R2, BT, NW, false, 0, NSTAGE, INPLACE>(p, rs, cube, pmap, n_frames, st);
     }
     return run_doppler_t<N, R1, R2, BT, NW, true, 0, NSTAGE, INPLACE>(p, rs, cube, pmap, n_frames, st);
+}
+
+// ---------------------------------------------------------------------------
+// fused front: K1 and K2 as the two roles of one cooperative persistent kernel (mmw_front.cuh)
+// ---------------------------------------------------------------------------
+template <int SN, int SR1, int SR2, int BT, int DN, int DR1, int DR2, int NW>
+static cudaError_t run_front_fused(const PlanDev &p, const int16_t *adc, float2 *rs, float *pmap, int n_frames, unsigned int *sync,
+                                   cudaStream_t st)
+{
+    const bool pads = p.S != SN, padc = p.C != DN;
+    using KernelT = void (*)(PlanDev, FrontArgs);
+    KernelT k = pads ? (padc ? front_fused_kernel<SN, SR1, SR2, BT, true, DN, DR1, DR2, true, NW>
+                             : front_fused_kernel<SN, SR1, SR2, BT, true, DN, DR1, DR2, false, NW>)
+                     : (padc ? front_fused_kernel<SN, SR1, SR2, BT, false, DN, DR1, DR2, true, NW>
+                             : front_fused_kernel<SN, SR1, SR2, BT, false, DN, DR1, DR2, false, NW>);
+    constexpr int bytes = FrontSmem<SN, BT, DN, DR1, DR2, NW>::kBytes;
+    static int per_sm_dev[kMaxDevices][4] = {{0}};
+    int &per_sm = per_sm_dev[current_device()][(pads ? 2 : 0) + (padc ? 1 : 0)];
+    if (!per_sm) {
+        cudaError_t e = resident_ctas(k, NW * 32, bytes, &per_sm);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 2) { per_sm = 0; return cudaErrorLaunchOutOfResources; }
+        if (per_sm > 512 / (NW * 32)) per_sm = 512 / (NW * 32);     // 16 warps per SM: what 128 registers per thread allow
+    }
+    const int sms = sm_count();
+    const int nrt = p.Sp / DopplerWarp<DN, DR1, DR2>::kRows;          // consumer tiles (= warps) per frame
+    const int nct = (p.C + BT - 1) / BT;                              // producer tiles per slab
+    int FG = (sms * 8) / nrt;                                         // frames the consumer role holds at a time: 8 of an SM's 16 warps
+    if (FG < 1) return cudaErrorInvalidConfiguration;
+    if (FG > n_frames) FG = n_frames;
+    FrontArgs g;
+    g.adc = adc; g.rs = rs; g.pmap = pmap;
+    g.produced = sync; g.consumed = sync + (size_t)n_frames * p.A;
+    g.n_frames = n_frames; g.FG = FG; g.stats = p.front_stats;
+    g.n_consumer_ctas = (FG * nrt + NW - 1) / NW;
+    const long long tiles = (long long)n_frames * p.A * nct;
+    long long nprod = (long long)per_sm * sms - g.n_consumer_ctas;
+    if (nprod > tiles) nprod = tiles;
+    if (nprod < 1) return cudaErrorInvalidConfiguration;
+    // slabs the producers hold in flight (a tile in work + one staged per CTA) + two antenna steps of the consumer group
+    const int inflight = (int)((2 * nprod + nct - 1) / nct);
+    g.window = p.front_window > 0 ? p.front_window : inflight + 2 * FG;
+    if (g.window < FG + 1) g.window = FG + 1;
+    cudaError_t e = cudaMemsetAsync(sync, 0, (size_t)2 * n_frames * p.A * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(g.n_consumer_ctas + nprod));
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;                      // every CTA resident at once: the roles wait for each other
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, p, g);
+}
+
+bool front_fused_supported(const PlanDev &p, int n_frames)
+{
+    if (p.keep_cube || p.base_adc != nullptr || p.A < 1) return false;
+    if (!((p.Sp == 512 && p.Cp == 256) || (p.Sp == 256 && p.Cp == 128))) return false;
+    // enough producer tiles to fill the grid a few times over; small batches keep the antenna-split path
+    return (long long)n_frames * p.A * ((p.C + 15) / 16) >= 8LL * sm_count();
+}
+
+cudaError_t launch_front_fused(const PlanDev &p, const int16_t *adc, float2 *rs, float *pmap, int n_frames, unsigned int *sync, cudaStream_t st)
+{
+    if (p.Sp == 512 && p.Cp == 256) {
+        // MMW_FRONT=3: 8-chirp producer tiles, 4 warps per CTA, four CTAs per SM (smaller barrier domains)
+        if (p.front_variant == 3) return run_front_fused<512, 16, 32, 8, 256, 16, 16, 4>(p, adc, rs, pmap, n_frames, sync, st);
+        return run_front_fused<512, 16, 32, 16, 256, 16, 16, 8>(p, adc, rs, pmap, n_frames, sync, st);
+    }
+    if (p.Sp == 256 && p.Cp == 128) return run_front_fused<256, 16, 16, 16, 128, 8, 16, 8>(p, adc, rs, pmap, n_frames, sync, st);
+    return cudaErrorInvalidValue;
 }
 
 bool plan_supported(int Sp, int Cp, const char **why)

@@ -253,6 +253,12 @@ int mmw_copy_cfar_mask(mmw_ctx *ctx, int frame, uint8_t *out);
 int mmw_time_device(mmw_ctx *ctx, const int16_t *adc_dev, int n_frames, int iters,
                     float *total_ms, float *per_stage_ms);
 
+/* Diagnostics of the fused front kernel (stages 1 and 2 as two roles of one kernel): with MMW_FRONT_STATS=1 in the
+ * environment at mmw_create, every CTA of the last launch leaves 8 uint64: {SM id | role << 32 (1 = range, 0 = Doppler),
+ * start ns, end ns, ns spent waiting for the other role, tiles / steps done, 0, 0, 0}.  Copies up to max_ctas records;
+ * returns the number copied, MMW_ERR_STATE without the switch. */
+int mmw_front_stats(mmw_ctx *ctx, unsigned long long *out, int max_ctas);
+
 #ifdef __cplusplus
 }
 #endif
