@@ -62,9 +62,22 @@ __host__ __device__ constexpr int ilog2(int n)
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }   // exact: a - b
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// a * w in two packed instructions: FMUL2 (w.y, w.x) * (-a.y, a.y), then FFMA2 w * (a.x, a.x) + that.  Written in this operand
+// order because ptxas folds swap and sign into the FIRST operand's modifiers (Rn.F32x2.LO_HI.NP) and the lane broadcast into the
+// second (Rm.F32): no register is moved, and a twiddle that lives in registers across a loop is kept in ONE (swapped) copy.
+// The roundings are those of fmaf(a.x, w.x, -(a.y * w.y)), fmaf(a.x, w.y, a.y * w.x).
 __device__ __forceinline__ float2 cmul(float2 a, float2 w)
 {
-    return make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.x, w.y, a.y * w.x));
+    const float2 t = __fmul2_rn(make_float2(w.y, w.x), make_float2(-a.y, a.y));
+    return __ffma2_rn(w, make_float2(a.x, a.x), t);
+}
+// d * (c - j s), c and s compile-time constants: (d.x c + d.y s, d.y c - d.x s) in two packed FMAs whose constants are
+// immediates (FFMA2 takes a broadcast 32-bit immediate, FMUL2 does not: hence the FMA with a zero addend for the product);
+// roundings: fmaf(d.x, c, d.y * s), fmaf(d.y, c, -(d.x * s)).
+__device__ __forceinline__ float2 crot(float2 d, float c, float s)
+{
+    const float2 t = __ffma2_rn(make_float2(d.y, -d.x), make_float2(s, s), make_float2(0.f, 0.f));
+    return __ffma2_rn(d, make_float2(c, c), t);
 }
 
 // (a - b) * exp(-j 2 pi K / 32), K in [0, 16), K known at compile time
@@ -75,19 +88,10 @@ __device__ __forceinline__ float2 sub_mul_w32(float2 a, float2 b)
         return csub(a, b);
     } else if constexpr (K == 8) {                       // * -j : (d.y, -d.x)
         return make_float2(a.y - b.y, b.x - a.x);
-    } else if constexpr (K == 4) {                       // * (1 - j)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        const float2 d = csub(a, b);
-        return make_float2((d.x + d.y) * h, (d.y - d.x) * h);
-    } else if constexpr (K == 12) {                      // * (-1 - j)/sqrt2
-        constexpr float h = 0.70710678118654752440f;
-        const float2 d = csub(a, b);
-        return make_float2((d.y - d.x) * h, -(d.x + d.y) * h);
-    } else {
+    } else {                                             // (K = 4, 12 included: c = +-s = 1/sqrt2)
         constexpr float c = w32_cos(K);
         constexpr float s = w32_sin(K);                  // w = c - j s
-        const float2 d = csub(a, b);
-        return make_float2(fmaf(d.x, c, d.y * s), fmaf(d.y, c, -d.x * s));
+        return crot(csub(a, b), c, s);
     }
 }
 

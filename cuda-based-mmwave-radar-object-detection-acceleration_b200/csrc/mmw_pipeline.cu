@@ -649,8 +649,8 @@ struct DopplerWarp {
     static constexpr int bytes(int nw, int nstage) { return kOffTw + 8 * N + nw * nstage * kStage * 8; }
 };
 
-template <int N, int R1, int R2, int NW, bool PAD, int SPT, int NSTAGE>
-__global__ void __launch_bounds__(NW * 32, 2) doppler_fft_warp_kernel(PlanDev p, const float2 *__restrict__ rs, float *__restrict__ pmap,
+template <int N, int R1, int R2, int NW, bool PAD, int SPT, int NSTAGE, int MINB = 2>
+__global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev p, const float2 *__restrict__ rs, float *__restrict__ pmap,
                                                                       int n_tiles)
 {
     static_assert(R1 * R2 == N, "plan");
@@ -938,10 +938,10 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
     return cudaGetLastError();
 }
 
-template <int N, int R1, int R2, int NW, bool PAD, int SPT, int NSTAGE>
+template <int N, int R1, int R2, int NW, bool PAD, int SPT, int NSTAGE, int MINB = 2>
 static cudaError_t run_doppler_warp_t(const PlanDev &p, const float2 *rs, float *pmap, int n_frames, cudaStream_t st)
 {
-    auto k = doppler_fft_warp_kernel<N, R1, R2, NW, PAD, SPT, NSTAGE>;
+    auto k = doppler_fft_warp_kernel<N, R1, R2, NW, PAD, SPT, NSTAGE, MINB>;
     using L = DopplerWarp<N, R1, R2>;
     constexpr int bytes = L::bytes(NW, NSTAGE);
     static int per_sm_dev[kMaxDevices] = {0};
@@ -958,14 +958,14 @@ static cudaError_t run_doppler_warp_t(const PlanDev &p, const float2 *rs, float 
     return cudaGetLastError();
 }
 
-template <int N, int R1, int R2, int NW, int SP0, int NSTAGE>
+template <int N, int R1, int R2, int NW, int SP0, int NSTAGE, int MINB = 2>
 static cudaError_t run_doppler_warp(const PlanDev &p, const float2 *rs, float *pmap, int n_frames, cudaStream_t st)
 {
     if (p.C == N) {
-        if (SP0 && p.Sp == SP0) return run_doppler_warp_t<N, R1, R2, NW, false, SP0, NSTAGE>(p, rs, pmap, n_frames, st);
-        return run_doppler_warp_t<N, R1, R2, NW, false, 0, NSTAGE>(p, rs, pmap, n_frames, st);
+        if (SP0 && p.Sp == SP0) return run_doppler_warp_t<N, R1, R2, NW, false, SP0, NSTAGE, MINB>(p, rs, pmap, n_frames, st);
+        return run_doppler_warp_t<N, R1, R2, NW, false, 0, NSTAGE, MINB>(p, rs, pmap, n_frames, st);
     }
-    return run_doppler_warp_t<N, R1, R2, NW, true, 0, NSTAGE>(p, rs, pmap, n_frames, st);
+    return run_doppler_warp_t<N, R1, R2, NW, true, 0, NSTAGE, MINB>(p, rs, pmap, n_frames, st);
 }
 
 template <int N, int R1, int R2, int BT, int NW, int SP0, int SP1, int NSTAGE = 2, bool INPLACE = false>
@@ -1113,6 +1113,11 @@ cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube,
         if (v == 1) return run_doppler<256, 16, 16, 8, 4, 512, 0, 2>(p, rs, cube, pmap, n_frames, st);
         if (v == 6) return run_doppler<256, 16, 16, 16, 8, 512, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
         if (v == 10 && !cube) return run_doppler_warp<256, 16, 16, 8, 512, 3>(p, rs, pmap, n_frames, st);
+        if (v == 13 && !cube) return run_doppler_warp<256, 16, 16, 10, 512, 2>(p, rs, pmap, n_frames, st);
+        if (v == 14 && !cube) return run_doppler_warp<256, 16, 16, 12, 512, 2>(p, rs, pmap, n_frames, st);
+        if (v == 15 && !cube) return run_doppler_warp<256, 16, 16, 6, 512, 2, 3>(p, rs, pmap, n_frames, st);
+        if (v == 16 && !cube) return run_doppler_warp<256, 16, 16, 5, 512, 2, 4>(p, rs, pmap, n_frames, st);
+        if (v == 17 && !cube) return run_doppler_warp<256, 16, 16, 6, 512, 3, 3>(p, rs, pmap, n_frames, st);
         // fused mode (power map only): warp-private tiles, 0.156 vs 0.171 ms on cfg3 (profiles/experiments/r1_k2_warp_private.log)
         if (v != 12 && !cube) return run_doppler_warp<256, 16, 16, 8, 512, 2>(p, rs, pmap, n_frames, st);
         return run_doppler<256, 16, 16, 16, 8, 512, 0>(p, rs, cube, pmap, n_frames, st);
