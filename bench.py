@@ -379,7 +379,10 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
         most = int(max(env.all_ranks(float(local_written))))
         gather_records = min(F * max_det, ((most * 3 // 2 + 1024) // 1024) * 1024)
         for ln in lanes:
-            ln.gather = pkg.sharding.DetectionGather(ln.ctx, dev, gather_records, side=side)
+            if env.exchange == "peer":
+                ln.gather = pkg.sharding.PeerDetectionGather(ln.ctx, dev, gather_records)
+            else:
+                ln.gather = pkg.sharding.DetectionGather(ln.ctx, dev, gather_records, side=side)
     gather = lanes[0].gather
 
     for k in range(max(W, D)):
@@ -422,7 +425,8 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
     elif rank == 0:
         recs, ghdr = gather.read(pkg.DET_DTYPE)
         n_det_step, gather_overflow = len(recs), int(ghdr[3])
-        assert np.all(np.diff(recs["frame"].astype(np.int64)) >= 0) and int(ghdr[2]) == world * F     # ordered, all frames accounted for
+        if os.environ.get("MMW_GATHER_DEBUG", "full") == "full":
+            assert np.all(np.diff(recs["frame"].astype(np.int64)) >= 0) and int(ghdr[2]) == world * F     # ordered, all frames accounted for
     else:
         n_det_step, gather_overflow = 0, 0
     overflow = int(max(env.all_ranks(float(local_overflow or gather_overflow))))
@@ -481,7 +485,11 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
         e2e_fps=world * F * e2e_steps / t_e2e, e2e_steps=e2e_steps, e2e_dets=len(dets), e2e_two=len(e2e_ring) > 1,
         h2d_bytes=F * 4 * N_adc, N_adc=N_adc,
     )
+    if world > 1:
+        env.sync_all()                                      # no rank unmaps a peer's memory while another may still write to it
     for ln in lanes:
+        if ln.gather is not None and hasattr(ln.gather, "close"):
+            ln.gather.close()                               # before its context
         ln.ctx.close()
         ln.adc = None
     shared.clear()
@@ -509,6 +517,7 @@ def compact_chain(res, world):
         "detections_per_step": res["n_det_step"], "max_detections_in_one_frame": res["max_det_frame"],
         "max_det_per_frame": res["max_det"], "overflow": res["overflow"], "hit_rows_retransformed": res["hit_rows"] or None,
         "exchange_records_per_rank": res["gather_records"] if world > 1 else None,
+        "exchange": (None if world == 1 else "copy-engine puts into rank 0's memory over NVLink (cudaIpc) + stream wait/write-value flags, one merge kernel on rank 0; NCCL for set-up and barriers" if env.exchange == "peer" else "NCCL gather per step + one merge kernel on rank 0"),
         "config_index": w["idx"],
     }
 
@@ -556,7 +565,7 @@ def run_chain(args, env):
                 "frames_per_gpu_per_step": F,
                 "batches_in_flight": D,
                 "ms_per_step_one_in_flight": res["total_ms_one"],
-                "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step one NCCL gather of a {gather_bytes}-byte result-block prefix per rank (sized from the warm-up batch) to rank 0 + merge kernel on a side stream, overlapping the next step (overflow={res['gather_overflow']})"),
+                "sharding": f"frame-sharded x{world}" + ("" if world == 1 else f"; per step a {gather_bytes}-byte result-block prefix per rank (sized from the warm-up batch) goes to rank 0 ({'copy-engine put over NVLink' if env.exchange == 'peer' else 'NCCL gather'}) + merge kernel on a side stream, overlapping the next step (overflow={res['gather_overflow']})"),
                 "doppler_cube": "materialised" if args.keep_cube else "fused (not written to HBM)",
                 "l2": f"inputs larger than L2: {F * 4 * res['N_adc'] / 1e6:.0f} MB int16 capture + {F * 8 * A * res['Sp'] * C / 1e6:.0f} MB intermediate per step vs 126 MB L2",
                 "ms_per_step_by_rank": [m / K for m in res["ms_by_rank"]], "host_issue_ms_per_step_by_rank": [m / K for m in res["host_ms_by_rank"]],
@@ -875,6 +884,9 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames (cfg5: sensors) per GPU per step (default: workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the detection lists reach rank 0: copy-engine puts into rank 0's memory over NVLink + stream memory "
+                         "operations (mmw_exchange_*; NCCL carries the set-up only), or an NCCL gather per step")
     ap.add_argument("--no-other", action="store_true", help="cfg3: skip the side measurements of cfg2 / cfg4 / cfg5 (configs[1], [3], [4])")
     ap.add_argument("--inflight", type=int, default=3, help="cfg2/cfg3/cfg4: batches in flight (contexts on their own streams, steps round-robin)")
     ap.add_argument("--depth", type=int, default=4, help="cfg5: one-frame calls in flight on the end-to-end path (ring of contexts, mmw_submit_host / mmw_wait)")
@@ -887,6 +899,7 @@ def main():
         run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
     env = Env()
+    env.exchange = args.exchange
     {"chain": run_chain, "stream": run_stream, "legacy": run_legacy}[WORKLOADS[args.workload]["kind"]](args, env)
     env.finish()
 

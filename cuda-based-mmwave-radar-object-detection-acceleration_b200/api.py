@@ -45,6 +45,8 @@ C_ABI_SYMBOLS = [
     "mmw_legacy_configure",
     "mmw_group_create", "mmw_group_destroy", "mmw_group_size", "mmw_group_context", "mmw_group_set_frame_offset", "mmw_shard_frames",
     "mmw_group_process_host", "mmw_group_process_device", "mmw_group_merged_block", "mmw_group_read_detections",
+    "mmw_exchange_create", "mmw_exchange_destroy", "mmw_exchange_handle", "mmw_exchange_connect", "mmw_exchange_put", "mmw_exchange_merge",
+    "mmw_exchange_wait",
 ]
 # the reference's own entry point (acceleration.h:32), C++ linkage
 LEGACY_MANGLED = "_Z14cudaProcessingPsP9Complex_tiPdS2_S2_S2_"
@@ -128,6 +130,14 @@ def load(build_if_missing: bool = True):
         getattr(L, name).argtypes = [vp, C.c_int, vp]
     L.mmw_time_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mmw_front_stats.argtypes = [vp, vp, C.c_int]
+    L.mmw_exchange_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.mmw_exchange_destroy.argtypes = [vp]
+    L.mmw_exchange_destroy.restype = None
+    L.mmw_exchange_handle.argtypes = [vp, vp]
+    L.mmw_exchange_connect.argtypes = [vp, vp]
+    L.mmw_exchange_put.argtypes = [vp]
+    L.mmw_exchange_merge.argtypes = [vp, C.POINTER(vp)]
+    L.mmw_exchange_wait.argtypes = [vp, vp, C.POINTER(vp)]
     L.mmw_set_graph_mode.argtypes = [vp, C.c_int]
     L.mmw_set_base_frame.argtypes = [vp, vp]
     L.mmw_process_capture_file.argtypes = [vp, C.c_char_p, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, ip, ip]
@@ -396,6 +406,50 @@ class RadarContext:
         if n < 0:
             _check(n)
         return out[:n]
+
+
+class PeerExchange:
+    """mmw_exchange_*: the gather of a frame-sharded job's detection lists by copy-engine puts into rank 0's memory
+    (include/mmw_radar.h).  `all_gather_bytes(b: bytes) -> list[bytes]` is the launcher's transport for the 64-byte handles."""
+
+    def __init__(self, ctx: "RadarContext", rank: int, n_ranks: int, records_per_rank: int, all_gather_bytes, depth: int = 4):
+        self._L = load()
+        self.ctx, self.rank, self.n_ranks, self.records_per_rank = ctx, rank, n_ranks, records_per_rank
+        h = C.c_void_p()
+        _check(self._L.mmw_exchange_create(ctx._h, rank, n_ranks, records_per_rank, depth, C.byref(h)))
+        self._x = h
+        mine = (C.c_ubyte * 64)()
+        _check(self._L.mmw_exchange_handle(self._x, mine))
+        everyone = all_gather_bytes(bytes(mine))
+        assert len(everyone) == n_ranks and all(len(b) == 64 for b in everyone)
+        blob = (C.c_ubyte * (64 * n_ranks)).from_buffer_copy(b"".join(everyone))
+        _check(self._L.mmw_exchange_connect(self._x, blob))
+
+    def close(self):
+        if getattr(self, "_x", None):
+            self._L.mmw_exchange_destroy(self._x)
+            self._x = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def put(self):
+        if not self.ctx._h.value or not self._x:
+            raise RadarError(MMW_ERR_STATE, "PeerExchange.put: the exchange or its context is closed")
+        _check(self._L.mmw_exchange_put(self._x))
+
+    def merge(self) -> int:
+        p = C.c_void_p()
+        _check(self._L.mmw_exchange_merge(self._x, C.byref(p)))
+        return p.value
+
+    def wait(self, cuda_stream: int | None = None) -> int:
+        p = C.c_void_p()
+        _check(self._L.mmw_exchange_wait(self._x, C.c_void_p(cuda_stream or 0), C.byref(p)))
+        return p.value
 
 
 class RadarGroup:

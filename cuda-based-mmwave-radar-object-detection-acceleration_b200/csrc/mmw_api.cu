@@ -325,6 +325,7 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     p.k1_variant = env_int("MMW_K1_VARIANT"); p.k2_variant = env_int("MMW_K2_VARIANT"); p.k3_variant = env_int("MMW_K3_VARIANT");
     p.k4_variant = env_int("MMW_K4_VARIANT"); p.ctas_per_sm_cap = env_int("MMW_CTAS_PER_SM");
     p.front_variant = env_int("MMW_FRONT"); p.front_window = env_int("MMW_FRONT_WINDOW");
+    p.reserve_ctas = env_int("MMW_RESERVE_CTAS");
     p.front_stats = nullptr;
     if (env_int("MMW_FRONT_STATS")) {
         if ((rc = dev_alloc(c, &c->d_front_stats, (size_t)kFrontStatsCtas * 8))) return fail(rc);
@@ -858,6 +859,201 @@ int mmw_merge_gathered(mmw_ctx *c, const void *gathered_dev, int n_ranks, long l
     CK(launch_merge((const unsigned char *)gathered_dev, n_ranks, (size_t)stride_bytes, (unsigned char *)merged_dev, merged_capacity, c->stream));
     return MMW_OK;
 }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer exchange: the gather of the detection lists of a frame-sharded job (one process per GPU) WITHOUT a kernel.
+// ---------------------------------------------------------------------------------------------------------------
+// The FFT kernels are persistent and fill every SM's register file, so any kernel of another stream — NCCL's send/recv
+// kernel included — waits for an FFT CTA to retire, then holds that slot while it waits for its peers, and the next FFT
+// kernel starts short of CTAs: measured +11 us per 0.40 ms step at 2 GPUs and +33 us at 8 for the NCCL gather
+// (profiles/r2/exchange.md).  Here every rank PUTS its result block straight into rank 0's memory with the copy engine
+// (cudaMemcpyAsync to a cudaIpc-mapped peer pointer: NVLink, no SM) and raises a flag in rank 0's memory with a stream
+// memory operation (cuStreamWriteValue32); rank 0's side stream waits for the flags (cuStreamWaitValue32) and runs the one
+// merge kernel; a credit written back the same way keeps a rank from overwriting a slot that is still being merged.
+// Set-up (exchange of the IPC handles) goes through whatever the launcher has — torch.distributed / NCCL in bench.py.
+typedef unsigned int (*StreamValueFn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);   // CUresult f(CUstream, CUdeviceptr, value, flags)
+
+struct mmw_exchange {
+    mmw_ctx *ctx;
+    int device;
+    int rank, n_ranks, depth;
+    long long stride;                 // bytes one rank contributes per step: header + records_per_rank records
+    int merged_cap;
+    // rank 0 owns: [depth][n_ranks][stride] gathered blocks, then n_ranks arrival counters (one allocation = one IPC handle)
+    unsigned char *gathered;          // rank 0: own allocation; others: mapped
+    unsigned int *arrival;            // inside the same allocation
+    unsigned char *merged[2];         // rank 0
+    unsigned int *credit;             // this rank's credit word (own allocation; rank 0 maps every rank's)
+    unsigned int *peer_credit[kMaxDevices];   // rank 0: mapped credit words of the other ranks
+    void *mapped_root;                // non-root: base of the mapped rank-0 allocation
+    cudaStream_t side;                // rank 0: wait + merge + credits
+    cudaEvent_t merged_ev[2];
+    unsigned int step;                // puts issued
+    unsigned int merges;              // merges issued (rank 0)
+    StreamValueFn wait_value, write_value;
+    int connected;
+};
+
+static size_t exchange_root_bytes(const mmw_exchange *x)
+{
+    return (size_t)x->depth * x->n_ranks * (size_t)x->stride + (size_t)kMaxDevices * sizeof(unsigned int);
+}
+
+extern "C" {
+
+void mmw_exchange_destroy(mmw_exchange *x)
+{
+    if (!x) return;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();                                          // (the context may already be gone: nothing of it is touched here)
+    if (x->rank == 0) {
+        for (int r = 1; r < x->n_ranks; ++r) if (x->peer_credit[r]) cudaIpcCloseMemHandle(x->peer_credit[r]);
+        cudaFree(x->gathered);
+        cudaFree(x->merged[0]); cudaFree(x->merged[1]);
+    } else if (x->mapped_root) {
+        cudaIpcCloseMemHandle(x->mapped_root);
+    }
+    cudaFree(x->credit);
+    for (auto &e : x->merged_ev) if (e) cudaEventDestroy(e);
+    if (x->side) cudaStreamDestroy(x->side);
+    delete x;
+}
+
+int mmw_exchange_create(mmw_ctx *c, int rank, int n_ranks, int records_per_rank, int depth, mmw_exchange **out)
+{
+    if (!c || !out) { set_last_error("mmw_exchange_create: null argument"); return MMW_ERR_ARG; }
+    *out = nullptr;
+    if (n_ranks < 1 || n_ranks > kMaxDevices || rank < 0 || rank >= n_ranks || depth < 2 || depth > 64 || records_per_rank < 1 ||
+        records_per_rank > c->dense_cap) {
+        set_last_error("mmw_exchange_create: bad rank / rank count / depth / records_per_rank");
+        return MMW_ERR_ARG;
+    }
+    CK(cudaSetDevice(c->device));
+    mmw_exchange *x = new mmw_exchange();
+    memset(x, 0, sizeof(*x));
+    x->ctx = c; x->device = c->device; x->rank = rank; x->n_ranks = n_ranks; x->depth = depth;
+    x->stride = kResultHeaderBytes + (long long)records_per_rank * (long long)sizeof(mmw_detection);
+    x->merged_cap = n_ranks * records_per_rank;
+    auto fail = [&](const char *what) { set_last_error("mmw_exchange_create: %s: %s", what, cudaGetErrorString(cudaGetLastError())); mmw_exchange_destroy(x); return MMW_ERR_CUDA; };
+    cudaDriverEntryPointQueryResult q;
+    void *fw = nullptr, *fs = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fw, cudaEnableDefault, &q) != cudaSuccess || !fw ||
+        cudaGetDriverEntryPoint("cuStreamWriteValue32", &fs, cudaEnableDefault, &q) != cudaSuccess || !fs)
+        return fail("stream memory operations are not available");
+    x->wait_value = (StreamValueFn)fw; x->write_value = (StreamValueFn)fs;
+    if (cudaMalloc((void **)&x->credit, 256) != cudaSuccess || cudaMemset(x->credit, 0, 256) != cudaSuccess) return fail("cudaMalloc");
+    if (rank == 0) {
+        const size_t bytes = exchange_root_bytes(x);
+        if (cudaMalloc((void **)&x->gathered, bytes) != cudaSuccess || cudaMemset(x->gathered, 0, bytes) != cudaSuccess) return fail("cudaMalloc");
+        x->arrival = reinterpret_cast<unsigned int *>(x->gathered + (size_t)depth * n_ranks * (size_t)x->stride);
+        const size_t mbytes = kResultHeaderBytes + (size_t)x->merged_cap * sizeof(mmw_detection);
+        for (auto &m : x->merged) if (cudaMalloc((void **)&m, mbytes) != cudaSuccess || cudaMemset(m, 0, mbytes) != cudaSuccess) return fail("cudaMalloc");
+        if (cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
+        for (auto &e : x->merged_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
+    }
+    CK(cudaDeviceSynchronize());
+    *out = x;
+    return MMW_OK;
+}
+
+/* 64 bytes: rank 0 -> the IPC handle of its gathered block; every other rank -> the IPC handle of its credit word */
+int mmw_exchange_handle(mmw_exchange *x, void *handle64)
+{
+    if (!x || !handle64) { set_last_error("mmw_exchange_handle: null argument"); return MMW_ERR_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(x->ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, x->rank == 0 ? (void *)x->gathered : (void *)x->credit));
+    memcpy(handle64, &h, sizeof(h));
+    return MMW_OK;
+}
+
+/* all_handles: n_ranks x 64 bytes, entry r = what rank r's mmw_exchange_handle returned */
+int mmw_exchange_connect(mmw_exchange *x, const void *all_handles)
+{
+    if (!x || !all_handles) { set_last_error("mmw_exchange_connect: null argument"); return MMW_ERR_ARG; }
+    CK(cudaSetDevice(x->ctx->device));
+    const cudaIpcMemHandle_t *h = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    if (x->rank == 0) {
+        for (int r = 1; r < x->n_ranks; ++r) {
+            void *p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h[r], cudaIpcMemLazyEnablePeerAccess));
+            x->peer_credit[r] = static_cast<unsigned int *>(p);
+        }
+    } else {
+        CK(cudaIpcOpenMemHandle(&x->mapped_root, h[0], cudaIpcMemLazyEnablePeerAccess));
+        x->gathered = static_cast<unsigned char *>(x->mapped_root);
+        x->arrival = reinterpret_cast<unsigned int *>(x->gathered + (size_t)x->depth * x->n_ranks * (size_t)x->stride);
+    }
+    x->connected = 1;
+    return MMW_OK;
+}
+
+/* After mmw_process_device, on the context's stream: this rank's result block goes to its slot of step `step` in rank 0's
+ * memory, then the arrival flag.  No kernel.  Blocks (on the stream, not the host) only if rank 0 is `depth` steps behind. */
+int mmw_exchange_put(mmw_exchange *x)
+{
+    if (!x || !x->connected) { set_last_error("mmw_exchange_put: not connected"); return MMW_ERR_STATE; }
+    mmw_ctx *c = x->ctx;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const unsigned int s = x->step++;
+    const int slot = (int)(s % (unsigned int)x->depth);
+    if (s >= (unsigned int)x->depth) {
+        // the slot was last used by step s - depth: rank 0 has merged it once the credit reads s - depth + 1
+        if (x->wait_value(st, (unsigned long long)(uintptr_t)x->credit, s - (unsigned int)x->depth + 1u, 0u /* GEQ */) != 0) {
+            set_last_error("mmw_exchange_put: cuStreamWaitValue32 failed");
+            return MMW_ERR_CUDA;
+        }
+    }
+    unsigned char *dst = x->gathered + ((size_t)slot * x->n_ranks + x->rank) * (size_t)x->stride;
+    CK(cudaMemcpyAsync(dst, c->d_result, (size_t)x->stride, cudaMemcpyDeviceToDevice, st));
+    if (x->write_value(st, (unsigned long long)(uintptr_t)(x->arrival + x->rank), s + 1u, 0u) != 0) {
+        set_last_error("mmw_exchange_put: cuStreamWriteValue32 failed");
+        return MMW_ERR_CUDA;
+    }
+    return MMW_OK;
+}
+
+/* Rank 0, once per step after its own put: the side stream waits for every rank's flag of that step, merges the blocks
+ * into one ordered list (one kernel), and hands the slot back.  Returns the merged block (device pointer; complete when the
+ * side stream gets there: mmw_exchange_wait makes a stream wait for it). */
+int mmw_exchange_merge(mmw_exchange *x, const void **merged_block)
+{
+    if (!x || !x->connected || x->rank != 0) { set_last_error("mmw_exchange_merge: rank 0 only, after connect"); return MMW_ERR_STATE; }
+    mmw_ctx *c = x->ctx;
+    CK(cudaSetDevice(c->device));
+    const unsigned int m = x->merges++;
+    if (m >= x->step) { x->merges--; set_last_error("mmw_exchange_merge: no put for this step yet"); return MMW_ERR_STATE; }
+    const int slot = (int)(m % (unsigned int)x->depth), k = (int)(m & 1u);
+    for (int r = 0; r < x->n_ranks; ++r)
+        if (x->wait_value(x->side, (unsigned long long)(uintptr_t)(x->arrival + r), m + 1u, 0u) != 0) { set_last_error("cuStreamWaitValue32 failed"); return MMW_ERR_CUDA; }
+    CK(launch_merge(x->gathered + (size_t)slot * x->n_ranks * (size_t)x->stride, x->n_ranks, (size_t)x->stride, x->merged[k], x->merged_cap, x->side));
+    CK(cudaEventRecord(x->merged_ev[k], x->side));
+    for (int r = 0; r < x->n_ranks; ++r) {
+        unsigned int *cr = r == 0 ? x->credit : x->peer_credit[r];
+        if (x->write_value(x->side, (unsigned long long)(uintptr_t)cr, m + 1u, 0u) != 0) { set_last_error("cuStreamWriteValue32 failed"); return MMW_ERR_CUDA; }
+    }
+    if (merged_block) *merged_block = x->merged[k];
+    return MMW_OK;
+}
+
+/* Rank 0: `cuda_stream` (nullptr: the context's stream) waits for the last merge issued; *merged_block is that block. */
+int mmw_exchange_wait(mmw_exchange *x, void *cuda_stream, const void **merged_block)
+{
+    if (!x || x->rank != 0 || x->merges == 0) { set_last_error("mmw_exchange_wait: rank 0 only, after a merge"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(x->ctx->device));
+    const int k = (int)((x->merges - 1u) & 1u);
+    CK(cudaStreamWaitEvent(cuda_stream ? (cudaStream_t)cuda_stream : x->ctx->stream, x->merged_ev[k], 0));
+    if (merged_block) *merged_block = x->merged[k];
+    return MMW_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 static int ensure_scratch(mmw_ctx *c, size_t bytes)
 {

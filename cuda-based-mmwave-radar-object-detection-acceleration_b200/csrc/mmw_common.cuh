@@ -30,6 +30,7 @@ struct PlanDev {
     // host-side only: kernel-shape overrides for the sweeps under profiles/ and the kernel-form parity tests.  Read ONCE, in
     // mmw_create (MMW_K1_VARIANT / MMW_K2_VARIANT / MMW_K3_VARIANT / MMW_K4_VARIANT / MMW_CTAS_PER_SM); 0 = pick by shape.
     int k1_variant, k2_variant, k3_variant, k4_variant, ctas_per_sm_cap;
+    int reserve_ctas;       // CTA slots the persistent FFT kernels leave free for kernels of other streams (mmw_reserve_ctas; MMW_RESERVE_CTAS)
     // MMW_FRONT: 0 = pick (fused front where supported), 1 = K1 and K2 as two kernels, 2 = fused front wherever supported;
     // MMW_FRONT_WINDOW: slabs the producer role may run ahead of the consumer role (0 = derived from the grid)
     int front_variant, front_window;

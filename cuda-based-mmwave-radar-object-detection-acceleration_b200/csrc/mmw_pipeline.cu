@@ -884,6 +884,17 @@ static int capped_per_sm(const PlanDev &p, int per_sm)
     return p.ctas_per_sm_cap > 0 && p.ctas_per_sm_cap < per_sm ? p.ctas_per_sm_cap : per_sm;
 }
 
+// Grid of a persistent FFT kernel: every resident CTA slot, less PlanDev.reserve_ctas (mmw_reserve_ctas).  The FFT kernels
+// fill an SM's register file, so a kernel of another stream that arrives while one runs — the NCCL kernel of the sharded
+// exchange, the merge kernel, the detection kernels of another batch in flight — finds no SM to start on until an FFT CTA
+// retires; slots left free let it start at once, at the price of reserve / (2 x 148) of the FFT throughput.
+static int persistent_grid(const PlanDev &p, int per_sm, long long work_items)
+{
+    long long slots = (long long)capped_per_sm(p, per_sm) * sm_count();
+    if (p.reserve_ctas > 0) slots = slots - p.reserve_ctas > sm_count() ? slots - p.reserve_ctas : (slots > sm_count() ? sm_count() : slots);
+    return (int)(work_items < slots ? work_items : slots);
+}
+
 template <int N, int R1, int R2, int BT, int NW, bool PAIR, bool PAD, int CT, int NSTAGE, bool BASE = false>
 static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs, int n_frames, cudaStream_t st)
 {
@@ -898,7 +909,7 @@ static cudaError_t run_range_t(const PlanDev &p, const int16_t *adc, float2 *rs,
     }
     const int nct = (p.C + BT - 1) / BT;
     const long long tiles = (long long)n_frames * p.A * nct;
-    const int grid = (int)(tiles < (long long)capped_per_sm(p, per_sm) * sm_count() ? tiles : (long long)capped_per_sm(p, per_sm) * sm_count());
+    const int grid = persistent_grid(p, per_sm, tiles);
     k<<<grid, NW * 32, bytes, st>>>(p, adc, rs, (int)tiles);
     return cudaGetLastError();
 }
@@ -933,7 +944,7 @@ static cudaError_t run_doppler_t(const PlanDev &p, const float2 *rs, float2 *cub
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     }
     const long long tiles = (long long)n_frames * (p.Sp / BT);
-    const int grid = (int)(tiles < (long long)capped_per_sm(p, per_sm) * sm_count() ? tiles : (long long)capped_per_sm(p, per_sm) * sm_count());
+    const int grid = persistent_grid(p, per_sm, tiles);
     k<<<grid, NW * 32, bytes, st>>>(p, rs, cube, pmap, (int)tiles);
     return cudaGetLastError();
 }
@@ -953,7 +964,7 @@ static cudaError_t run_doppler_warp_t(const PlanDev &p, const float2 *rs, float 
     }
     const long long tiles = (long long)n_frames * (p.Sp / L::kRows);
     const long long want = (tiles + NW - 1) / NW;
-    const int grid = (int)(want < (long long)capped_per_sm(p, per_sm) * sm_count() ? want : (long long)capped_per_sm(p, per_sm) * sm_count());
+    const int grid = persistent_grid(p, per_sm, want);
     k<<<grid, NW * 32, bytes, st>>>(p, rs, pmap, (int)tiles);
     return cudaGetLastError();
 }

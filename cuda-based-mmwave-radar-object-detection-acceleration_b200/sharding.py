@@ -13,6 +13,8 @@ Works with the nccl backend (CUDA tensors) and with gloo (CPU tensors; used by t
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 REC_BYTES = 24
@@ -125,6 +127,11 @@ class DetectionGather:
         k = self.step & 1
         self.step += 1
         compute = torch.cuda.current_stream()
+        dbg = os.environ.get("MMW_GATHER_DEBUG", "full")          # experiment switch: which parts of the exchange run
+        if dbg != "full" and self.rank == 0:
+            self.latest = self.merged[k]                          # (not a result: the timing experiment only)
+        if dbg == "none":
+            return self.latest if self.rank == 0 else None
         if self.done[k] is not None:
             compute.wait_event(self.done[k])                      # two steps old: never actually waits
         self.send[k].copy_(self.local)
@@ -132,8 +139,9 @@ class DetectionGather:
         dst = dist.get_global_rank(self.group, 0) if self.group is not None else 0
         with torch.cuda.stream(self.side):
             self.side.wait_event(self.snap[k])
-            dist.gather(self.send[k], gather_list=self.slots[k] if self.rank == 0 else None, dst=dst, group=self.group)
-            if self.rank == 0:
+            if dbg != "snap":
+                dist.gather(self.send[k], gather_list=self.slots[k] if self.rank == 0 else None, dst=dst, group=self.group)
+            if self.rank == 0 and dbg == "full":
                 self.ctx.use_stream(self.side.cuda_stream)
                 self.ctx.merge_gathered(self.gathered[k], self.world, self.stride, self.merged[k], self.merged_cap)
                 self.ctx.use_stream(compute.cuda_stream)
@@ -158,6 +166,58 @@ class DetectionGather:
         header = m[:32].view(np.uint32).copy()
         n = int(header[0])
         return np.frombuffer(m[32:32 + REC_BYTES * n].tobytes(), dtype=det_dtype), header
+
+
+class PeerDetectionGather:
+    """The exchange step without a kernel on the data path (mmw_exchange_*, include/mmw_radar.h): every rank's result block
+    goes straight into rank 0's memory over NVLink by a copy-engine put, flags and credits are stream memory operations, and
+    rank 0 runs the one merge kernel on a side stream.  torch.distributed (NCCL) only carries the 64-byte IPC handles at
+    set-up.  Same interface as DetectionGather: run() after ctx.process_device() on the context's stream, flush(), read()."""
+
+    def __init__(self, ctx, device, records_per_rank: int, group=None, depth: int = 4):
+        import torch
+        import torch.distributed as dist
+
+        from .api import PeerExchange
+
+        self.torch, self.ctx, self.device = torch, ctx, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.records_per_rank = records_per_rank
+
+        def all_gather_bytes(b: bytes):
+            mine = torch.tensor(list(b), dtype=torch.uint8, device=device)
+            everyone = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(everyone, mine, group=group)
+            return [bytes(t.cpu().tolist()) for t in everyone]
+
+        self.x = PeerExchange(ctx, self.rank, self.world, records_per_rank, all_gather_bytes, depth=depth)
+        self.merged_bytes = 32 + REC_BYTES * self.world * records_per_rank
+        self.latest = None
+        dist.barrier(group=group)                                  # every rank is connected before the first put
+
+    def run(self):
+        self.x.put()
+        if self.rank == 0:
+            self.latest = self.x.merge()
+        return self.latest
+
+    def flush(self):
+        """the context's stream waits for the last merge (rank 0); returns the merged block's device pointer"""
+        if self.rank == 0 and self.latest is not None:
+            self.latest = self.x.wait(self.ctx.stream)
+        return self.latest
+
+    def read(self, det_dtype):
+        """rank 0: (records, header) of the last merged block on the host (synchronises)"""
+        self.flush()
+        self.torch.cuda.synchronize(self.device)
+        m = device_bytes_view(self.latest, self.merged_bytes, self.device).cpu().numpy()
+        header = m[:32].view(np.uint32).copy()
+        n = int(header[0])
+        return np.frombuffer(m[32:32 + REC_BYTES * n].tobytes(), dtype=det_dtype), header
+
+    def close(self):
+        self.x.close()
 
 
 def records_from_bytes(buf, det_dtype) -> np.ndarray:

@@ -253,6 +253,24 @@ int mmw_copy_cfar_mask(mmw_ctx *ctx, int frame, uint8_t *out);
 int mmw_time_device(mmw_ctx *ctx, const int16_t *adc_dev, int n_frames, int iters,
                     float *total_ms, float *per_stage_ms);
 
+/* ---- the exchange step of a frame-sharded job with ONE PROCESS PER GPU, without a kernel ----
+ * The reference has no multi-GPU path (cudaBenchMarking.cpp:374-378 feeds one frame at a time to one GPU).  Every rank puts a
+ * fixed-size prefix of its result block ([32-byte header | records_per_rank records], mmw_device_result_block) straight into
+ * rank 0's memory over NVLink with the copy engine (a cudaIpc-mapped peer pointer) and raises an arrival counter there with a
+ * stream memory operation; rank 0's side stream waits for the counters, runs the one merge kernel (as mmw_merge_gathered)
+ * and writes a credit back so that a slot is not overwritten while it is being merged (`depth` steps may be in flight).
+ * No NCCL kernel competes with the persistent FFT kernels for an SM.  Set-up: create on every rank, exchange the 64-byte
+ * handles with any transport (bench.py: torch.distributed all_gather over NCCL), connect.  Per step, on every rank after
+ * mmw_process_device: mmw_exchange_put; on rank 0 also mmw_exchange_merge.  All calls are asynchronous. */
+typedef struct mmw_exchange mmw_exchange;
+int mmw_exchange_create(mmw_ctx *ctx, int rank, int n_ranks, int records_per_rank, int depth, mmw_exchange **out);
+void mmw_exchange_destroy(mmw_exchange *x);
+int mmw_exchange_handle(mmw_exchange *x, void *handle64);                 /* 64 bytes out */
+int mmw_exchange_connect(mmw_exchange *x, const void *all_handles);       /* n_ranks x 64 bytes, in rank order */
+int mmw_exchange_put(mmw_exchange *x);                                    /* on the context's stream */
+int mmw_exchange_merge(mmw_exchange *x, const void **merged_block);       /* rank 0: [32-byte header | ordered records], device */
+int mmw_exchange_wait(mmw_exchange *x, void *cuda_stream, const void **merged_block);   /* rank 0: stream waits for the last merge */
+
 /* Diagnostics of the fused front kernel (stages 1 and 2 as two roles of one kernel): with MMW_FRONT_STATS=1 in the
  * environment at mmw_create, every CTA of the last launch leaves 8 uint64: {SM id | role << 32 (1 = range, 0 = Doppler),
  * start ns, end ns, ns spent waiting for the other role, tiles / steps done, 0, 0, 0}.  Copies up to max_ctas records;

@@ -1,9 +1,13 @@
 """Worker of tests/test_gpu_multi.py: run under torchrun with one rank per GPU.  Every rank processes its contiguous
-frame block of the same seeded batch, the detection lists are gathered to rank 0 with sharding.DetectionGather (NCCL +
-merge kernel, several pipelined steps), and rank 0 compares the merged list with the list one GPU computes for the whole
-batch.  Exit code 0 = byte-identical."""
+frame block of the same seeded batch, the detection lists are gathered to rank 0 — argv[1] = "nccl": sharding.DetectionGather
+(NCCL gather + merge kernel), "peer": sharding.PeerDetectionGather (copy-engine puts into rank 0's memory, mmw_exchange_*) —
+over several pipelined steps (more than the exchange's ring depth), and rank 0 compares the merged list with the list one
+GPU computes for the whole batch.  Exit code 0 = byte-identical."""
+import faulthandler
 import os
 import sys
+
+faulthandler.enable()
 
 import numpy as np
 import torch
@@ -28,9 +32,10 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     ctx.use_stream(stream.cuda_stream)
     mine = torch.from_numpy(adc[first:first + cnt]).to(dev)
-    gather = pkg.sharding.DetectionGather(ctx, dev, 4096)
+    mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
+    gather = pkg.sharding.PeerDetectionGather(ctx, dev, 4096) if mode == "peer" else pkg.sharding.DetectionGather(ctx, dev, 4096)
     with torch.cuda.stream(stream):
-        for _ in range(3):                                        # several steps: exercises the double buffering
+        for _ in range(11):                                       # several steps: exercises the double buffering / the slot ring
             ctx.process_device(mine, cnt)
             gather.run()
         gather.flush()
@@ -41,7 +46,10 @@ def main():
         with pkg.RadarContext(S, C, A, F, device=local) as whole:
             want, _ = whole.process_host(adc, F)
         ok = recs.tobytes() == want.tobytes() and int(hdr[0]) == len(want) and int(hdr[2]) == F and int(hdr[3]) == 0
-        print(f"world {world}: {len(recs)} gathered detections, match={ok}", flush=True)
+        print(f"world {world} ({mode}): {len(recs)} gathered detections, match={ok}", flush=True)
+    dist.barrier()
+    if mode == "peer":
+        gather.close()
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()

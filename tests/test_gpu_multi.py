@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_nccl_gather_equals_single_gpu():
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_gather_equals_single_gpu(mode):
+    """nccl: NCCL gather per step; peer: copy-engine puts into rank 0's memory (mmw_exchange_*), NCCL for the set-up only"""
     import torch
 
     n = torch.cuda.device_count()
@@ -19,7 +21,7 @@ def test_nccl_gather_equals_single_gpu():
         pytest.skip("needs two GPUs")
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gather_check.py")]
+           "--master-port", "29533" if mode == "nccl" else "29534", os.path.join(ROOT, "tests", "dist_gather_check.py"), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "match=True" in r.stdout
