@@ -482,6 +482,8 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
         b_alg=int(ctx.info.algorithmic_bytes_per_frame), kernels_per_batch=int(ctx.info.kernels_per_batch),
         n_det_step=n_det_step, max_det_frame=int(frame_counts.max()), max_det=max_det, overflow=overflow, hit_rows=hit_rows,
         gather_records=gather_records, gather_overflow=gather_overflow,
+        exchange=(None if world == 1 else "copy-engine puts into rank 0's memory over NVLink (cudaIpc) + stream wait/write-value flags, one merge kernel on rank 0; "
+                  "NCCL for set-up and barriers" if env.exchange == "peer" else "NCCL gather per step + one merge kernel on rank 0"),
         e2e_fps=world * F * e2e_steps / t_e2e, e2e_steps=e2e_steps, e2e_dets=len(dets), e2e_two=len(e2e_ring) > 1,
         h2d_bytes=F * 4 * N_adc, N_adc=N_adc,
     )
@@ -517,7 +519,7 @@ def compact_chain(res, world):
         "detections_per_step": res["n_det_step"], "max_detections_in_one_frame": res["max_det_frame"],
         "max_det_per_frame": res["max_det"], "overflow": res["overflow"], "hit_rows_retransformed": res["hit_rows"] or None,
         "exchange_records_per_rank": res["gather_records"] if world > 1 else None,
-        "exchange": (None if world == 1 else "copy-engine puts into rank 0's memory over NVLink (cudaIpc) + stream wait/write-value flags, one merge kernel on rank 0; NCCL for set-up and barriers" if env.exchange == "peer" else "NCCL gather per step + one merge kernel on rank 0"),
+        "exchange": res["exchange"],
         "config_index": w["idx"],
     }
 

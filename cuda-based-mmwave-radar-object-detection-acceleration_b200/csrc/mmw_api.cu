@@ -69,6 +69,7 @@ struct mmw_ctx {
     uint32_t *d_offsets;
     unsigned int *d_ticket;
     unsigned long long *d_front_stats;   // MMW_FRONT_STATS=1 only
+    unsigned int *d_sched;        // PlanDev.sched
     unsigned int *d_front_sync;   // produced / consumed slab counters of the fused front kernel, [2][max_frames * A]
     uint4 *d_rows;            // hit rows of the selective Doppler re-FFT (wide arrays, fused mode)
     float2 *d_snap;           // antenna snapshots of the detected cells (same path)
@@ -202,7 +203,7 @@ void mmw_destroy(mmw_ctx *c)
     cudaSetDevice(c->device);
     cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
     cudaFree(c->d_adc); cudaFree(c->d_base); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_psplit); cudaFree(c->d_mask);
-    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_front_sync); cudaFree(c->d_front_stats); cudaFree(c->d_rows); cudaFree(c->d_snap); cudaFree(c->d_result); cudaFree(c->d_scratch);
+    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_front_sync); cudaFree(c->d_sched); cudaFree(c->d_front_stats); cudaFree(c->d_rows); cudaFree(c->d_snap); cudaFree(c->d_result); cudaFree(c->d_scratch);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto &h : c->h_ring) if (h) cudaFreeHost(h);
     for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
@@ -282,6 +283,8 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     if ((rc = dev_alloc(c, &c->d_offsets, (size_t)F + 1))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_ticket, (size_t)4))) return fail(rc);
     if ((rc = dev_alloc(c, &c->d_front_sync, (size_t)2 * F * A))) return fail(rc);
+    if ((rc = dev_alloc(c, &c->d_sched, (size_t)8))) return fail(rc);
+    if (cudaMemset(c->d_sched, 0, 8 * sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     if (cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     c->dense_cap = F * cfg->max_det_per_frame;
     // wide arrays without a Doppler cube: snapshots of the detected cells come from a selective re-FFT of the hit rows
@@ -321,11 +324,13 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     p.alpha = cfg->cfar_alpha; p.lambda_over_d = cfg->lambda_over_d;
     p.max_det = cfg->max_det_per_frame; p.keep_cube = cfg->keep_doppler_cube ? 1 : 0; p.frame_offset = 0;
     p.base_adc = nullptr;
+    p.sched = c->d_sched;
     // kernel-shape overrides of the sweeps under profiles/ and of the kernel-form parity tests: read once, here
     p.k1_variant = env_int("MMW_K1_VARIANT"); p.k2_variant = env_int("MMW_K2_VARIANT"); p.k3_variant = env_int("MMW_K3_VARIANT");
     p.k4_variant = env_int("MMW_K4_VARIANT"); p.ctas_per_sm_cap = env_int("MMW_CTAS_PER_SM");
     p.front_variant = env_int("MMW_FRONT"); p.front_window = env_int("MMW_FRONT_WINDOW");
     p.reserve_ctas = env_int("MMW_RESERVE_CTAS");
+    p.sched_dynamic = getenv("MMW_SCHED") ? env_int("MMW_SCHED") : 1;
     p.front_stats = nullptr;
     if (env_int("MMW_FRONT_STATS")) {
         if ((rc = dev_alloc(c, &c->d_front_stats, (size_t)kFrontStatsCtas * 8))) return fail(rc);

@@ -26,10 +26,12 @@ struct PlanDev {
     const float2 *tw1_r;    // [Sp]  pass-1 twiddles of the range FFT in consumption order (tw1_index)
     const float2 *tw1_d;    // [Cp]  pass-1 twiddles of the Doppler FFT in consumption order
     const float2 *tw_a;     // [n_theta]
+    unsigned int *sched;    // [8] work counters of the persistent FFT kernels: {next item, CTAs retired} for K1 at [0], K2 at [2]; zero between launches
     const int16_t *base_adc; // one frame [C][A][S] IIQQ subtracted before the range window, or nullptr (static-clutter removal)
     // host-side only: kernel-shape overrides for the sweeps under profiles/ and the kernel-form parity tests.  Read ONCE, in
     // mmw_create (MMW_K1_VARIANT / MMW_K2_VARIANT / MMW_K3_VARIANT / MMW_K4_VARIANT / MMW_CTAS_PER_SM); 0 = pick by shape.
     int k1_variant, k2_variant, k3_variant, k4_variant, ctas_per_sm_cap;
+    int sched_dynamic;      // bit 0: K1, bit 1: K2 take their tiles from PlanDev.sched instead of a fixed stride (MMW_SCHED; default 1)
     int reserve_ctas;       // CTA slots the persistent FFT kernels leave free for kernels of other streams (mmw_reserve_ctas; MMW_RESERVE_CTAS)
     // MMW_FRONT: 0 = pick (fused front where supported), 1 = K1 and K2 as two kernels, 2 = fused front wherever supported;
     // MMW_FRONT_WINDOW: slabs the producer role may run ahead of the consumer role (0 = derived from the grid)

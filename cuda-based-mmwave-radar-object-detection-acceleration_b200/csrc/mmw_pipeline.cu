@@ -41,6 +41,17 @@ void plan_radices(int n, int *r1, int *r2)
     }
 }
 
+// Work counters of the persistent FFT kernels (PlanDev.sched: {next item, CTAs retired} per kernel).  The last CTA to retire puts
+// both back to zero for the next launch on the stream (launches that share a counter pair are stream-ordered).
+__device__ __forceinline__ void sched_retire(unsigned int *ctr)
+{
+    __threadfence();
+    if (atomicAdd(&ctr[1], 1u) == gridDim.x - 1u) {
+        ctr[0] = 0u;
+        ctr[1] = 0u;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K1: range FFT
 // ---------------------------------------------------------------------------
@@ -109,6 +120,12 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
         }
     };
 
+    // Tiles are handed out by a counter (PlanDev.sched), not by a fixed stride: a CTA that starts late — its SM was still held by
+    // a kernel of another stream (another batch in flight, the exchange's merge kernel) — simply takes fewer tiles instead of
+    // finishing its fixed share late.  The first tile of a CTA is blockIdx.x; the next one is fetched while pass 1 runs.
+    const bool DYN = NSTAGE == 1 && (p.sched_dynamic & 1);
+    __shared__ int s_next[2];
+    unsigned int *ctr = p.sched;                                      // [0] next tile - gridDim.x, [1] CTAs done
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -125,11 +142,13 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
     int it = 0;                                                       // tiles done by this CTA
 
 #pragma unroll 1
-    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (; tile < n_tiles; ++it) {
         const int ct = tile % nct, fa = tile / nct;
         const int c0 = ct * BT;
         const bool row_ok = c0 + row < C;
         const float wdop = row_ok ? p.win_d[c0 + row] : 0.f;
+        unsigned int fetched = 0u;
+        if (DYN && tid == 0) fetched = atomicAdd(&ctr[0], 1u);        // answer needed after pass 1 only
         if (NSTAGE == 2 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
         mbar_wait(&bar[it % NSTAGE], (uint32_t)((it / NSTAGE) & 1));
         const unsigned char *srow = stage + (it % NSTAGE) * L::kStageBytes + row * L::kStageStride;
@@ -210,12 +229,14 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
                 }
             }
         }
+        if (DYN && tid == 0) s_next[(it + 1) & 1] = (int)min(fetched + gridDim.x, (unsigned int)n_tiles);
         __syncthreads();
+        const int next_tile = DYN ? s_next[(it + 1) & 1] : tile + (int)gridDim.x;
         // single staging buffer: it is consumed now, prefetch the next tile behind pass 2.  (Refilling it earlier — as
         // soon as the last warp has pulled its pass-1 inputs into registers — removes the wait on the copy but not a
         // microsecond of run time: the stall moves to the barrier, profiles/experiments/r1_k1_early_release.md.  L2 prefetch
         // hints for the tiles after that made it slower, r1_k1_l2_prefetch.log.)
-        if (NSTAGE == 1 && warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, it + 1);
+        if (NSTAGE == 1 && warp == 0 && next_tile < n_tiles) issue(next_tile, it + 1);
 
         // ---- pass 2: R1 butterflies of radix R2 on contiguous runs; outputs go straight to HBM ----
         float2 *out = rs + (size_t)fa * (size_t)N * C + c0 + row;
@@ -237,7 +258,9 @@ __global__ void __launch_bounds__(NW * 32, (2 * RangeSmem<N, BT, NSTAGE, BASE>::
             }
         }
         __syncthreads();
+        tile = next_tile;
     }
+    if (DYN && tid == 0) sched_retire(ctr);
 }
 
 // ---------------------------------------------------------------------------
@@ -308,11 +331,28 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
 
     // a "step" is one antenna of one tile; the q-th step of this CTA is antenna q % A of its (q / A)-th tile, and
     // steps of consecutive tiles are pipelined back to back
+    // Tiles are handed out by a counter (PlanDev.sched[2], see range_fft_kernel): the CTA's first tile is blockIdx.x, the
+    // tile of ordinal o > 0 is gridDim.x + the counter's value when warp 0 asked.  Warp 0, which issues the staging copies up
+    // to two tiles ahead of the transform, keeps the answers in a four-entry queue in shared memory; its request for the next
+    // ordinal is in flight while the current one is staged, so nobody waits for the atomic.
+    __shared__ int s_tileq[4];
+    unsigned int *ctr = p.sched + 2;
+    const bool dyn = (p.sched_dynamic & 2) != 0;                       // else: the fixed stride gridDim.x
+    unsigned int pending = 0u;                                        // warp 0, lane 0: answer for ordinal `stored`
+    int stored = 1;                                                   // ordinals < stored are in the queue
     auto issue_step = [&](int q) {                                    // warp 0
         const int itq = q / A, a = q - itq * A;
-        const long long tl = (long long)blockIdx.x + (long long)itq * gridDim.x;
-        if (tl >= n_tiles) return;
-        const int tile = (int)tl;
+        if (itq >= stored) {                                          // first step of a new ordinal (they come in order)
+            if (lane == 0) {
+                const unsigned int t = dyn ? pending + gridDim.x : blockIdx.x + (unsigned int)itq * gridDim.x;
+                s_tileq[itq & 3] = (int)(t < (unsigned int)n_tiles ? t : (unsigned int)n_tiles);
+                if (dyn) pending = atomicAdd(&ctr[0], 1u);
+            }
+            ++stored;
+            __syncwarp();
+        }
+        const int tile = s_tileq[itq & 3];
+        if (tile >= n_tiles) return;
         const int rt = tile % nrt, f = tile / nrt;
         const int buf = q % NSTAGE;
         uint64_t *b = &bar[buf];
@@ -333,9 +373,12 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
 #pragma unroll
         for (int i = 0; i < NSTAGE; ++i) mbar_init(&bar[i], 1);
         fence_mbar_init();
+        s_tileq[0] = (int)min(blockIdx.x, (unsigned int)n_tiles);
+        if (dyn) pending = atomicAdd(&ctr[0], 1u);                    // ordinal 1
     }
     __syncthreads();
-    int tile = blockIdx.x;
+    int tile = s_tileq[0];
+    int ord = 0;
     if (warp == 0) {
 #pragma unroll
         for (int i = 0; i < AHEAD; ++i) issue_step(i);
@@ -353,7 +396,7 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
     }
 
 #pragma unroll 1
-    for (; tile < n_tiles; tile += gridDim.x) {
+    for (; tile < n_tiles; tile = s_tileq[++ord & 3]) {              // (warp 0 queued the next ordinal at least one barrier ago)
         const int rt = tile % nrt, f = tile / nrt;
         const int r0 = rt * BT;
         float acc[UPS2][R2];
@@ -430,6 +473,10 @@ __global__ void __launch_bounds__(NW * 32, doppler_min_ctas<N, BT, NW, NSTAGE, I
                 for (int k2 = 0; k2 < R2; ++k2) o[(size_t)(R1 * k2) * Sp] = acc[ui][k2];
             }
         }
+    }
+    if (dyn) {
+        __syncthreads();
+        if (tid == 0) sched_retire(ctr);
     }
 }
 
@@ -672,9 +719,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
     const int nrt = Sp / ROWS;
     const long long gw = (long long)blockIdx.x * NW + warp, nwarp = (long long)gridDim.x * NW;
 
+    // Tiles are handed out by a counter (PlanDev.sched[2]): a warp's first tile is its global index, every later one is
+    // nwarp + the counter's value when the warp asked — a warp of a CTA that started late takes fewer tiles.  The staging copies
+    // run NSTAGE - 1 steps ahead, i.e. up to two tiles ahead of the one being transformed, so a warp knows its next two tiles
+    // (t1, t2); the request for the one after is issued when a tile starts and collected when it ends.
+    unsigned int *ctr = p.sched + 2;
+    const bool dyn = (p.sched_dynamic & 2) != 0;                     // else: the fixed stride nwarp
+    auto request = [&]() -> unsigned int { return dyn && lane == 0 ? atomicAdd(&ctr[0], 1u) : 0u; };
+    auto collect = [&](unsigned int r, long long prev) -> long long { return dyn ? nwarp + (long long)__shfl_sync(0xffffffffu, r, 0) : prev + nwarp; };
+    long long t0 = gw, t1, t2;                                      // tiles of ordinals ord0, ord0 + 1, ord0 + 2
+    int ord0 = 0;
+    {
+        const unsigned int r1 = request(), r2 = request();
+        t1 = collect(r1, t0);
+        t2 = collect(r2, t1);
+    }
+
     auto issue_step = [&](int q) {                                  // the q-th step of this warp
         const int itq = q / A, a = q - itq * A;
-        const long long tl = gw + (long long)itq * nwarp;
+        const int d = itq - ord0;                                   // 0, 1 or 2
+        const long long tl = d == 0 ? t0 : (d == 1 ? t1 : t2);
         if (tl >= n_tiles) return;
         const int tile = (int)tl;
         const int rt = tile % nrt, f = tile / nrt;
@@ -710,9 +774,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
 
     int q = 0;
 #pragma unroll 1
-    for (long long tl = gw; tl < n_tiles; tl += nwarp) {
-        const int tile = (int)tl;
+    while (t0 < n_tiles) {
+        const int tile = (int)t0;
         const int rt = tile % nrt, f = tile / nrt;
+        const unsigned int req = request();                         // tile of ordinal ord0 + 3: collected when this tile ends
         float acc[U2][R2];
 #pragma unroll
         for (int u = 0; u < U2; ++u)
@@ -774,6 +839,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
 #pragma unroll
             for (int k2 = 0; k2 < R2; ++k2) po[(size_t)(k1 + R1 * k2) * Sp] = acc[u][k2];
         }
+        t0 = t1;
+        t1 = t2;
+        t2 = collect(req, t2);
+        ++ord0;
+    }
+    if (dyn) {
+        __syncthreads();
+        if (tid == 0) sched_retire(ctr);
     }
 }
 

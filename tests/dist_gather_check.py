@@ -27,13 +27,13 @@ def main():
     S, C, A, F = 256, 128, 4, 11                                  # 11 frames: uneven shards
     adc = pkg.synth.cube_batch(F, S, C, A, cfg=2, n_targets=6)
     first, cnt = pkg.sharding.shard_frames(F, world, rank)
-    ctx = pkg.RadarContext(S, C, A, max(cnt, 1), device=local)
+    ctx = pkg.RadarContext(S, C, A, max(cnt, 1), max_det_per_frame=2048, device=local)       # capacity >= the exchange's 2048 records on every rank
     ctx.set_frame_offset(first)
     stream = torch.cuda.Stream(device=dev)
     ctx.use_stream(stream.cuda_stream)
     mine = torch.from_numpy(adc[first:first + cnt]).to(dev)
     mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
-    gather = pkg.sharding.PeerDetectionGather(ctx, dev, 4096) if mode == "peer" else pkg.sharding.DetectionGather(ctx, dev, 4096)
+    gather = pkg.sharding.PeerDetectionGather(ctx, dev, 2048) if mode == "peer" else pkg.sharding.DetectionGather(ctx, dev, 2048)
     with torch.cuda.stream(stream):
         for _ in range(11):                                       # several steps: exercises the double buffering / the slot ring
             ctx.process_device(mine, cnt)
@@ -43,7 +43,7 @@ def main():
     ok = True
     if rank == 0:
         recs, hdr = gather.read(pkg.DET_DTYPE)
-        with pkg.RadarContext(S, C, A, F, device=local) as whole:
+        with pkg.RadarContext(S, C, A, F, max_det_per_frame=2048, device=local) as whole:
             want, _ = whole.process_host(adc, F)
         ok = recs.tobytes() == want.tobytes() and int(hdr[0]) == len(want) and int(hdr[2]) == F and int(hdr[3]) == 0
         print(f"world {world} ({mode}): {len(recs)} gathered detections, match={ok}", flush=True)
