@@ -272,6 +272,12 @@ __device__ __forceinline__ float accumulate_power(float acc, float2 v)
 {
     return __fadd_rn(acc, __fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)));
 }
+// two bins at once: each |X|^2 with the roundings above, the two running sums as one packed add (same bits, one issue slot less)
+__device__ __forceinline__ float2 accumulate_power2(float2 acc, float2 v0, float2 v1)
+{
+    const float2 pw = make_float2(__fmaf_rn(v0.x, v0.x, __fmul_rn(v0.y, v0.y)), __fmaf_rn(v1.x, v1.x, __fmul_rn(v1.y, v1.y)));
+    return __fadd2_rn(acc, pw);
+}
 
 // INPLACE: pass 1 writes its outputs back into the staging row it read (a thread reads and writes the same R1
 // addresses, so there is no hazard), which frees the separate work buffer: the same footprint then holds three
@@ -727,30 +733,43 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
     const bool dyn = (p.sched_dynamic & 2) != 0;                     // else: the fixed stride nwarp
     auto request = [&]() -> unsigned int { return dyn && lane == 0 ? atomicAdd(&ctr[0], 1u) : 0u; };
     auto collect = [&](unsigned int r, long long prev) -> long long { return dyn ? nwarp + (long long)__shfl_sync(0xffffffffu, r, 0) : prev + nwarp; };
-    long long t0 = gw, t1, t2;                                      // tiles of ordinals ord0, ord0 + 1, ord0 + 2
-    int ord0 = 0;
+    long long t0 = gw, t1, t2;                                      // the tile being transformed and the next two of this warp
     {
         const unsigned int r1 = request(), r2 = request();
         t1 = collect(r1, t0);
         t2 = collect(r2, t1);
     }
 
-    auto issue_step = [&](int q) {                                  // the q-th step of this warp
-        const int itq = q / A, a = q - itq * A;
-        const int d = itq - ord0;                                   // 0, 1 or 2
-        const long long tl = d == 0 ? t0 : (d == 1 ? t1 : t2);
-        if (tl >= n_tiles) return;
+    // Staging side.  The ROWS rows of a tile are neighbours in rs ([f][a][Sp][C]), so one step is ONE bulk copy of ROWS * C
+    // elements, issued by lane 0: the rows land back to back at the head of the ring slot (row i at i * C), pass 1 pulls them
+    // into registers and writes its outputs over them in the padded layout (row i at i * kRowStride).  The step to stage next
+    // is running state — its antenna, its tile (is_d-th after the one being transformed), its ring slot, its source address —
+    // advanced by additions; the only division left is one per tile.
+    const uint32_t step_bytes = (uint32_t)(ROWS * C * 8);
+    const size_t ant_stride = (size_t)Sp * C;                       // float2 between the antennas of one (frame, range bin)
+    auto tile_src = [&](long long tl) -> const float2 * {
         const int tile = (int)tl;
         const int rt = tile % nrt, f = tile / nrt;
-        uint64_t *b = &bar[q % NSTAGE];
-        if (lane == 0) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(b, (uint32_t)(ROWS * C * 8));
+        return rs + ((size_t)f * A * Sp + (size_t)rt * ROWS) * (size_t)C;
+    };
+    int is_a = 0, is_d = 0, is_slot = 0;                            // is_d: 0, 1 or 2 (the copies run NSTAGE - 1 <= 2 steps ahead)
+    const float2 *is_src = rs;
+    auto issue_next = [&]() {
+        const long long tl = is_d == 0 ? t0 : (is_d == 1 ? t1 : t2);
+        if (tl < n_tiles) {
+            if (is_a == 0) is_src = tile_src(tl);
+            if (lane == 0) {
+                uint64_t *b = &bar[is_slot];
+                fence_proxy_async();
+                mbar_arrive_expect_tx(b, step_bytes);
+                bulk_g2s(ring + (size_t)is_slot * L::kStage, is_src, step_bytes, b);
+            }
+            is_src += ant_stride;
         }
-        __syncwarp();
-        if (lane < ROWS) {
-            const float2 *src = rs + (((size_t)f * A + a) * Sp + rt * ROWS + lane) * (size_t)C;
-            bulk_g2s(ring + (size_t)(q % NSTAGE) * L::kStage + lane * L::kRowStride, src, (uint32_t)(C * 8), b);
+        is_slot = is_slot + 1 == NSTAGE ? 0 : is_slot + 1;
+        if (++is_a == A) {
+            is_a = 0;
+            ++is_d;
         }
     };
 
@@ -762,7 +781,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
     for (int i = tid; i < N; i += NW * 32) tw[i] = p.tw1_d[i];
     __syncthreads();                                                 // the only CTA-wide barrier
 #pragma unroll
-    for (int i = 0; i < NSTAGE - 1; ++i) issue_step(i);
+    for (int i = 0; i < NSTAGE - 1; ++i) issue_next();
 
     float2 twr[TWREG ? U1 : 1][TWREG ? R1 - 1 : 1];
     if constexpr (TWREG) {
@@ -777,18 +796,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
     while (t0 < n_tiles) {
         const int tile = (int)t0;
         const int rt = tile % nrt, f = tile / nrt;
-        const unsigned int req = request();                         // tile of ordinal ord0 + 3: collected when this tile ends
-        float acc[U2][R2];
+        const unsigned int req = request();                         // the tile after t2: collected when this tile ends
+        float2 acc[U2][R2 / 2];                                     // bins k2 = 2 j, 2 j + 1
 #pragma unroll
         for (int u = 0; u < U2; ++u)
 #pragma unroll
-            for (int j = 0; j < R2; ++j) acc[u][j] = 0.f;
+            for (int j = 0; j < R2 / 2; ++j) acc[u][j] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
         for (int a = 0; a < A; ++a, ++q) {
-            issue_step(q + NSTAGE - 1);                              // into the buffer step q - 1 has just left
+            issue_next();                                            // step q + NSTAGE - 1, into the slot step q - 1 has just left
             mbar_wait(&bar[q % NSTAGE], (uint32_t)((q / NSTAGE) & 1));
-            float2 *r = ring + (size_t)(q % NSTAGE) * L::kStage + row * L::kRowStride;
+            float2 *slot = ring + (size_t)(q % NSTAGE) * L::kStage;
+            const float2 *rin = slot + row * C;                      // as staged
+            float2 *r = slot + row * L::kRowStride;                  // as transformed
 
             // pass 1: all inputs into registers first (the outputs overwrite other threads' inputs)
             float2 x[U1][R1];
@@ -798,7 +819,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
 #pragma unroll
                 for (int m = 0; m < R1; ++m) {
                     const int n = n2 + m * R2;
-                    x[u][m] = (!PAD || n < C) ? r[n] : make_float2(0.f, 0.f);
+                    x[u][m] = (!PAD || n < C) ? rin[n] : make_float2(0.f, 0.f);
                 }
             }
             __syncwarp();
@@ -824,10 +845,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
                 for (int n2 = 0; n2 < R2; ++n2) y[n2] = wi[n2];
                 dft_regs<R2>(y);
 #pragma unroll
-                for (int k2 = 0; k2 < R2; ++k2) {
-                    const float2 v = y[bitrev(k2, LR2)];
-                    acc[u][k2] = accumulate_power(acc[u][k2], v);
-                }
+                for (int j = 0; j < R2 / 2; ++j) acc[u][j] = accumulate_power2(acc[u][j], y[bitrev(2 * j, LR2)], y[bitrev(2 * j + 1, LR2)]);
             }
             __syncwarp();
         }
@@ -837,12 +855,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) doppler_fft_warp_kernel(PlanDev
         for (int u = 0; u < U2; ++u) {
             const int k1 = sub + u * SUBS;
 #pragma unroll
-            for (int k2 = 0; k2 < R2; ++k2) po[(size_t)(k1 + R1 * k2) * Sp] = acc[u][k2];
+            for (int j = 0; j < R2 / 2; ++j) {
+                po[(size_t)(k1 + R1 * (2 * j)) * Sp] = acc[u][j].x;
+                po[(size_t)(k1 + R1 * (2 * j + 1)) * Sp] = acc[u][j].y;
+            }
         }
         t0 = t1;
         t1 = t2;
         t2 = collect(req, t2);
-        ++ord0;
+        --is_d;
     }
     if (dyn) {
         __syncthreads();

@@ -88,3 +88,24 @@ def test_file_entry_points_report_a_missing_file(pkg, tmp_path):
 def test_legacy_distance_from_raw_is_the_reference_formula(pkg, orc):
     for raw in (0, 1, 127, 1966, 6552):
         assert pkg.api.legacy_distance_from_raw(raw) == orc.lib().orc_distance_from_raw(raw, 12800, 16384)
+
+
+def test_register_butterfly_networks_against_a_direct_dft(tmp_path):
+    """csrc/fft_regs.cuh compiled for the HOST (its packed arithmetic spelled with fmaf): every radix the kernels use,
+    impulse / the reference's ramp vector (acceleration.cu:361-365) / random int16-range inputs, against a direct fp64 DFT
+    with the reference's sign convention (cudaBenchMarking.cpp:88-104).  No GPU involved: nvcc is only the compiler."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "dft_regs_host_check")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([nvcc, "-ccbin", cxx, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-o", exe,
+                    os.path.join(root, "tests", "dft_regs_host_check.cu")], check=True, capture_output=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    errs = {int(l.split()[0]): float(l.split()[1]) for l in res.stdout.splitlines()}
+    assert res.returncode == 0 and sorted(errs) == [2, 4, 8, 16, 32], res.stdout + res.stderr
+    assert max(errs.values()) < 2e-6      # tolerance: a few fp32 ulps of the largest output bin (measured 1.1e-7 at radix 32)
