@@ -1229,6 +1229,9 @@ cudaError_t launch_doppler_fft(const PlanDev &p, const float2 *rs, float2 *cube,
     }
     // 512 points: 8-row tiles, in place, three staging buffers = 103 KB, two CTAs per SM: 0.76 ms against 1.00 ms for the
     // 16-row double-buffered shape (201 KB, one CTA per SM) on the cfg4 cube (profiles/experiments/r1_cfg4_tile_sweep.log)
+    // (warp-private tiles at 512 points — 2 rows x 16 lanes, two radix-16 butterflies per lane in pass 1, one radix-32 in pass 2,
+    // 165 registers, 12 warps per SM — measured 1.32-1.69 ms against 0.69 on the cfg4 cube: profiles/r2/sweep_k2_warp_512_128.log)
+    // four warps per 8-row tile (every slot busy in both passes; 2 or 3 CTAs per SM): 0.80-0.81 ms, same log
     case 512:  return run_doppler<512, 16, 32, 8, 8, 1024, 0, 3, true>(p, rs, cube, pmap, n_frames, st);
     case 1024: return run_doppler<1024, 32, 32, 8, 8, 0, 0>(p, rs, cube, pmap, n_frames, st);
     default:   return cudaErrorInvalidValue;
