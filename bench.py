@@ -196,8 +196,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * T / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        # the GPU arm's workload keys under the GPU arm's names; a step here is a bounded sample of that workload
         "config": {"workload": workload_text(args.workload) if w["kind"] == "legacy" else chain_workload_text(args.workload),
-                   "frames_per_step": per_step},
+                   "frames_per_gpu_per_step": args.frames or w["F"], "sample_frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": used, "kind": kind,
                          "sample": f"{per_step} frames per step x {len(times)} steps, {what}, {used} thread(s)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -38,7 +38,7 @@ C_ABI_SYMBOLS = [
     "mmw_set_windows", "mmw_get_windows", "mmw_set_frame_offset", "mmw_stream", "mmw_use_stream",
     "mmw_process_device", "mmw_process_host", "mmw_submit_host", "mmw_wait", "mmw_read_detections", "mmw_read_counts",
     "mmw_device_results", "mmw_device_result_block", "mmw_merge_gathered", "mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map",
-    "mmw_copy_cfar_mask", "mmw_time_device", "mmw_front_stats",
+    "mmw_copy_cfar_mask", "mmw_time_device", "mmw_front_stats", "mmw_check_guards",
     "mmw_set_graph_mode", "mmw_set_base_frame", "mmw_process_capture_file", "mmw_default_radar_params", "mmw_to_physical",
     "mmw_legacy_process_frame", "mmw_legacy_process_frames", "mmw_legacy_copy_spectrum", "mmw_legacy_shutdown",
     "mmw_legacy_process_device", "mmw_legacy_sync", "mmw_legacy_distance_from_raw", "mmw_legacy_process_file",
@@ -130,6 +130,7 @@ def load(build_if_missing: bool = True):
         getattr(L, name).argtypes = [vp, C.c_int, vp]
     L.mmw_time_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mmw_front_stats.argtypes = [vp, vp, C.c_int]
+    L.mmw_check_guards.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.mmw_exchange_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.mmw_exchange_destroy.argtypes = [vp]
     L.mmw_exchange_destroy.restype = None
@@ -178,6 +179,11 @@ def _check(rc: int, allow_overflow: bool = False) -> int:
     if rc == MMW_OK or (allow_overflow and rc == MMW_ERR_OVERFLOW):
         return rc
     raise RadarError(rc, load().mmw_last_error().decode(errors="replace"))
+
+
+def last_error() -> str:
+    """Text of the last error (or guard-band report) of the calling thread: mmw_last_error()."""
+    return load().mmw_last_error().decode(errors="replace")
 
 
 def _np_ptr(a: np.ndarray):
@@ -398,6 +404,13 @@ class RadarContext:
         _check(self._L.mmw_time_device(self._h, C.c_void_p(_dev_ptr(adc_dev)), n_frames, iters, C.byref(total),
                                        stages if per_stage else None))
         return (total.value, list(stages)) if per_stage else total.value
+
+    def check_guards(self) -> int:
+        """Guard bytes overwritten around the context's device buffers since create (needs MMW_GUARD=1 at create): 0 = no
+        kernel wrote out of bounds.  include/mmw_radar.h: mmw_check_guards."""
+        bad = C.c_longlong(0)
+        _check(self._L.mmw_check_guards(self._h, C.byref(bad)))
+        return int(bad.value)
 
     def front_stats(self, max_ctas: int = 1024) -> np.ndarray:
         """Per-CTA record of the last fused-front launch (MMW_FRONT_STATS=1 at create): [n, 8] uint64."""

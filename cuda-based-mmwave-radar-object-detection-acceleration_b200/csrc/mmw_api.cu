@@ -78,6 +78,12 @@ struct mmw_ctx {
     uint32_t *d_header;
     void *d_scratch;         // export scratch
     size_t scratch_bytes;
+    // MMW_GUARD=1 at mmw_create: every device buffer of the context sits between two kGuardBytes bands filled with kGuardByte;
+    // mmw_check_guards reads them back (compute-sanitizer's memcheck is not available on every pool: this catches any
+    // out-of-bounds WRITE of any kernel of the chain, at the granularity of one byte past either end)
+    int guard_on;
+    struct GuardedBuf { unsigned char *base; void *user; size_t bytes; const char *name; };
+    std::vector<GuardedBuf> *guards;
     // pinned host
     unsigned char *h_result;  // pinned mirror of d_result
     uint32_t *h_header;
@@ -134,13 +140,42 @@ static int env_int(const char *name)
         }                                                                                                 \
     } while (0)
 
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardByte = 0xA5;
+
 template <typename T>
-static int dev_alloc(mmw_ctx *c, T **p, size_t count)
+static int dev_alloc_named(mmw_ctx *c, T **p, size_t count, const char *name)
 {
-    const size_t bytes = count * sizeof(T);
-    CK(cudaMalloc((void **)p, bytes ? bytes : 16));
+    size_t bytes = count * sizeof(T);
+    if (!bytes) bytes = 16;
+    if (c->guard_on) {
+        unsigned char *base = nullptr;
+        CK(cudaMalloc((void **)&base, bytes + 2 * kGuardBytes));
+        CK(cudaMemset(base, kGuardByte, kGuardBytes));
+        CK(cudaMemset(base + kGuardBytes + bytes, kGuardByte, kGuardBytes));
+        *p = reinterpret_cast<T *>(base + kGuardBytes);
+        c->guards->push_back({base, (void *)*p, bytes, name});
+    } else {
+        CK(cudaMalloc((void **)p, bytes));
+    }
     c->workspace_bytes += bytes;
     return MMW_OK;
+}
+#define dev_alloc(c, p, count) dev_alloc_named(c, p, count, #p)
+
+// cudaFree of a buffer that came from dev_alloc (its guard bands go with it)
+static void dev_free(mmw_ctx *c, void *user)
+{
+    if (!user) return;
+    if (c->guard_on && c->guards) {
+        for (size_t i = 0; i < c->guards->size(); ++i)
+            if ((*c->guards)[i].user == user) {
+                cudaFree((*c->guards)[i].base);
+                c->guards->erase(c->guards->begin() + (long)i);
+                return;
+            }
+    }
+    cudaFree(user);
 }
 
 static std::vector<float2> make_twiddles(int n)
@@ -201,9 +236,12 @@ void mmw_destroy(mmw_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_win_r); cudaFree(c->d_win_d); cudaFree(c->d_tw1_r); cudaFree(c->d_tw1_d); cudaFree(c->d_tw_d); cudaFree(c->d_tw_a);
-    cudaFree(c->d_adc); cudaFree(c->d_base); cudaFree(c->d_rs); cudaFree(c->d_cube); cudaFree(c->d_pmap); cudaFree(c->d_psplit); cudaFree(c->d_mask);
-    cudaFree(c->d_noise); cudaFree(c->d_keys); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_ticket); cudaFree(c->d_front_sync); cudaFree(c->d_sched); cudaFree(c->d_front_stats); cudaFree(c->d_rows); cudaFree(c->d_snap); cudaFree(c->d_result); cudaFree(c->d_scratch);
+    void *bufs[] = {c->d_win_r, c->d_win_d, c->d_tw1_r, c->d_tw1_d, c->d_tw_d, c->d_tw_a, c->d_adc, c->d_base, c->d_rs, c->d_cube, c->d_pmap,
+                    c->d_psplit, c->d_mask, c->d_noise, c->d_keys, c->d_counts, c->d_offsets, c->d_ticket, c->d_front_sync, c->d_sched,
+                    c->d_front_stats, c->d_rows, c->d_snap, c->d_result};
+    for (void *b : bufs) dev_free(c, b);
+    cudaFree(c->d_scratch);
+    delete c->guards;
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto &h : c->h_ring) if (h) cudaFreeHost(h);
     for (auto &e : c->chunk_ev) if (e) cudaEventDestroy(e);
@@ -256,6 +294,8 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     c->cfg = *cfg;
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
+    c->guard_on = env_int("MMW_GUARD") ? 1 : 0;
+    c->guards = new std::vector<mmw_ctx::GuardedBuf>();
     int rc = MMW_OK;
     auto fail = [&](int code) { mmw_destroy(c); return code; };
 
@@ -1142,6 +1182,33 @@ int mmw_front_stats(mmw_ctx *c, unsigned long long *out, int max_ctas)
     const int n = max_ctas < kFrontStatsCtas ? max_ctas : kFrontStatsCtas;
     CK(cudaMemcpy(out, c->d_front_stats, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return n;
+}
+
+int mmw_check_guards(mmw_ctx *c, long long *bad_bytes)
+{
+    if (!c || !bad_bytes) { set_last_error("mmw_check_guards: null argument"); return MMW_ERR_ARG; }
+    *bad_bytes = 0;
+    if (!c->guard_on) { set_last_error("mmw_check_guards: the context was not created with MMW_GUARD=1"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned char> h(2 * kGuardBytes);
+    long long bad = 0;
+    char first[160] = "";
+    for (const auto &g : *c->guards) {
+        CK(cudaMemcpy(h.data(), g.base, kGuardBytes, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h.data() + kGuardBytes, g.base + kGuardBytes + g.bytes, kGuardBytes, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < 2 * kGuardBytes; ++i)
+            if (h[i] != (unsigned char)kGuardByte) {
+                if (!bad)
+                    snprintf(first, sizeof first, "%s (%zu bytes): byte %lld %s", g.name, g.bytes,
+                             i < kGuardBytes ? (long long)kGuardBytes - (long long)i : (long long)(i - kGuardBytes),
+                             i < kGuardBytes ? "before its start" : "past its end");
+                ++bad;
+            }
+    }
+    *bad_bytes = bad;
+    if (bad) set_last_error("mmw_check_guards: %lld guard bytes overwritten; first: %s", bad, first);
+    return MMW_OK;
 }
 
 int mmw_time_device(mmw_ctx *c, const int16_t *adc_dev, int n_frames, int iters, float *total_ms, float *per_stage_ms)

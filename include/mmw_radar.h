@@ -253,6 +253,15 @@ int mmw_copy_cfar_mask(mmw_ctx *ctx, int frame, uint8_t *out);
 int mmw_time_device(mmw_ctx *ctx, const int16_t *adc_dev, int n_frames, int iters,
                     float *total_ms, float *per_stage_ms);
 
+/* Guard bands (a memcheck of our own; compute-sanitizer is not available on every pool): a context created with MMW_GUARD=1 in
+ * the environment brackets every device buffer it owns (range spectrum, cube, power map, mask, noise, keys, counts, result
+ * block, tables, staging, ...) with two 4 KB bands of a known byte.  mmw_check_guards synchronises the device, reads the bands
+ * back and writes the number of overwritten guard bytes to *bad_bytes (0 = no kernel of the chain wrote out of bounds since
+ * mmw_create; mmw_last_error() names the first buffer hit otherwise).  Returns MMW_ERR_STATE on a context created without
+ * the switch.  The reference has no such check; its cudaDataExtension_kernel leaves element 12 800 uninitialised and its
+ * reshape kernel reads out of bounds (acceleration.cu:152-166, 117-150). */
+int mmw_check_guards(mmw_ctx *ctx, long long *bad_bytes);
+
 /* ---- the exchange step of a frame-sharded job with ONE PROCESS PER GPU, without a kernel ----
  * The reference has no multi-GPU path (cudaBenchMarking.cpp:374-378 feeds one frame at a time to one GPU).  Every rank puts a
  * fixed-size prefix of its result block ([32-byte header | records_per_rank records], mmw_device_result_block) straight into
