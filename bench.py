@@ -40,7 +40,9 @@ METRIC = "radar frames/sec (ADC cube->detections)"
 WORKLOADS = {
     # name: kind, S, C, A, frames per GPU per step, BASELINE.json config index
     "cfg3": dict(kind="chain", S=512, C=256, A=12, F=64, idx=2),
-    "cfg2": dict(kind="chain", S=256, C=128, A=4, F=1024, idx=1),
+    # detect_path=2 (MMW_DETECT_REFFT): 83 k detections per batch — the hit rows are re-transformed once instead of a DFT per
+    # detection (list + measure 0.135 -> 0.08 ms; profiles/r2/sweep_k4x_narrow.log); the other shapes keep the library's default
+    "cfg2": dict(kind="chain", S=256, C=128, A=4, F=1024, idx=1, detect_path=2),
     "cfg4": dict(kind="chain", S=1024, C=512, A=192, F=4, idx=3),
     "cfg5": dict(kind="stream", S=256, C=128, A=12, F=64, idx=4),
     "cfg1": dict(kind="legacy", S=100, C=128, A=4, F=4096, idx=0),
@@ -334,6 +336,8 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
     class Lane:
         def __init__(self, i):
             self.ctx = pkg.RadarContext(S, C, A, F, keep_doppler_cube=keep_cube, max_det_per_frame=max_det, device=env.local_rank)
+            if w.get("detect_path"):
+                self.ctx.set_detect_path(w["detect_path"])
             first_frame = (i * world + rank) * F              # weak scaling: every rank owns F frames of each global batch
             self.ctx.set_frame_offset(first_frame)
             if share_input and "adc" in shared:
@@ -414,10 +418,10 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
     ms = max(ms_by_rank)
     frame_counts = ctx.read_counts(F)                       # true per-frame hit counts of this rank's last batch
     hdr = header_view.view(torch.int32).cpu().numpy()
-    # wide arrays in fused mode re-transform every (frame, range bin) that has hits (doppler_extract_kernel): those rows of the
-    # range spectrum are read once more, A * C * 8 bytes each
+    # the re-FFT detection path (wide arrays in fused mode, or detect_path=2) re-transforms every (frame, range bin) that has
+    # hits (doppler_extract_kernel): those rows of the range spectrum are read once more, A * C * 8 bytes each
     hit_rows = 0
-    if A >= 32 and not keep_cube and int(ctx.info.kernels_per_batch) == 7:
+    if not keep_cube and int(ctx.info.kernels_per_batch) == 7:
         last = pkg.sharding.records_from_bytes(pkg.sharding.device_bytes_view(dense_ptr, 24 * int(hdr[0]), dev), pkg.DET_DTYPE)
         hit_rows = len(np.unique(last["frame"].astype(np.int64) << 16 | last["range_bin"]))
     local_overflow = int(hdr[3]) or int(frame_counts.max() > max_det)
@@ -521,6 +525,7 @@ def compact_chain(res, world):
         "max_det_per_frame": res["max_det"], "overflow": res["overflow"], "hit_rows_retransformed": res["hit_rows"] or None,
         "exchange_records_per_rank": res["gather_records"] if world > 1 else None,
         "exchange": res["exchange"],
+        "detect_path": {0: "auto", 1: "per-cell", 2: "re-FFT of the hit rows (mmw_set_detect_path)"}[w.get("detect_path", 0)],
         "config_index": w["idx"],
     }
 
@@ -576,6 +581,7 @@ def run_chain(args, env):
                 "rank0_numa_node": env.numa,
                 "detections_per_step": res["n_det_step"], "max_detections_in_one_frame": res["max_det_frame"],
                 "max_det_per_frame": res["max_det"], "overflow": res["overflow"], "hit_rows_retransformed": res["hit_rows"] or None,
+                "detect_path": {0: "auto", 1: "per-cell", 2: "re-FFT of the hit rows (mmw_set_detect_path)"}[w.get("detect_path", 0)],
             },
             "roofline": {
                 "bound": "hbm", "kernel": STAGE_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

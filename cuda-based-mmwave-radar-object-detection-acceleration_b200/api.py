@@ -38,7 +38,7 @@ C_ABI_SYMBOLS = [
     "mmw_set_windows", "mmw_get_windows", "mmw_set_frame_offset", "mmw_stream", "mmw_use_stream",
     "mmw_process_device", "mmw_process_host", "mmw_submit_host", "mmw_wait", "mmw_read_detections", "mmw_read_counts",
     "mmw_device_results", "mmw_device_result_block", "mmw_merge_gathered", "mmw_copy_range_spectrum", "mmw_copy_doppler_cube", "mmw_copy_power_map",
-    "mmw_copy_cfar_mask", "mmw_time_device", "mmw_front_stats", "mmw_check_guards",
+    "mmw_copy_cfar_mask", "mmw_time_device", "mmw_front_stats", "mmw_check_guards", "mmw_set_detect_path",
     "mmw_set_graph_mode", "mmw_set_base_frame", "mmw_process_capture_file", "mmw_default_radar_params", "mmw_to_physical",
     "mmw_legacy_process_frame", "mmw_legacy_process_frames", "mmw_legacy_copy_spectrum", "mmw_legacy_shutdown",
     "mmw_legacy_process_device", "mmw_legacy_sync", "mmw_legacy_distance_from_raw", "mmw_legacy_process_file",
@@ -131,6 +131,7 @@ def load(build_if_missing: bool = True):
     L.mmw_time_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.mmw_front_stats.argtypes = [vp, vp, C.c_int]
     L.mmw_check_guards.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.mmw_set_detect_path.argtypes = [vp, C.c_int]
     L.mmw_exchange_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.mmw_exchange_destroy.argtypes = [vp]
     L.mmw_exchange_destroy.restype = None
@@ -179,6 +180,9 @@ def _check(rc: int, allow_overflow: bool = False) -> int:
     if rc == MMW_OK or (allow_overflow and rc == MMW_ERR_OVERFLOW):
         return rc
     raise RadarError(rc, load().mmw_last_error().decode(errors="replace"))
+
+
+DETECT_AUTO, DETECT_PER_CELL, DETECT_REFFT = 0, 1, 2      # MMW_DETECT_* of include/mmw_radar.h
 
 
 def last_error() -> str:
@@ -282,6 +286,12 @@ class RadarContext:
     def set_graph_mode(self, enable: bool):
         """Replay the launch sequence of a batch as one CUDA graph (for one-frame-per-call streaming)."""
         _check(self._L.mmw_set_graph_mode(self._h, int(bool(enable))))
+
+    def set_detect_path(self, path: int):
+        """DETECT_AUTO / DETECT_PER_CELL / DETECT_REFFT: how fused mode gets the antenna snapshots of the detected cells
+        (include/mmw_radar.h: mmw_set_detect_path)."""
+        _check(self._L.mmw_set_detect_path(self._h, int(path)))
+        _check(self._L.mmw_get_info(self._h, C.byref(self.info)))      # kernels_per_batch and workspace_bytes follow the path
 
     def set_frame_offset(self, first_frame: int):
         _check(self._L.mmw_set_frame_offset(self._h, int(first_frame)))

@@ -255,6 +255,19 @@ void mmw_destroy(mmw_ctx *c)
     delete c;
 }
 
+// buffers of the selective Doppler re-FFT detection path (hit rows, antenna snapshots of the detected cells); no-op in cube
+// mode, when they exist already, or when the snapshots would exceed 2 GB (the per-detection kernels are used then)
+static int alloc_refft_buffers(mmw_ctx *c)
+{
+    const size_t A = (size_t)c->cfg.n_antennas;
+    if (c->cfg.keep_doppler_cube || c->d_snap != nullptr) return MMW_OK;
+    if ((size_t)c->dense_cap * A * sizeof(float2) > ((size_t)2 << 30)) return MMW_OK;
+    int rc;
+    if ((rc = dev_alloc(c, &c->d_rows, (size_t)c->cfg.max_frames * next_pow2(c->cfg.n_samples)))) return rc;
+    if ((rc = dev_alloc(c, &c->d_snap, (size_t)c->dense_cap * A))) return rc;
+    return MMW_OK;
+}
+
 int mmw_create(const mmw_config *cfg, mmw_ctx **out)
 {
     if (!cfg || !out) { set_last_error("mmw_create: null argument"); return MMW_ERR_ARG; }
@@ -328,11 +341,9 @@ int mmw_create(const mmw_config *cfg, mmw_ctx **out)
     if (cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)) != cudaSuccess) { set_last_error("cudaMemset failed"); return fail(MMW_ERR_CUDA); }
     c->dense_cap = F * cfg->max_det_per_frame;
     // wide arrays without a Doppler cube: snapshots of the detected cells come from a selective re-FFT of the hit rows
-    // (launch_detect); its buffers scale with the detection capacity — beyond 2 GB the per-detection kernel is used instead
-    if (A >= 32 && !cfg->keep_doppler_cube && (size_t)c->dense_cap * A * sizeof(float2) <= ((size_t)2 << 30)) {
-        if ((rc = dev_alloc(c, &c->d_rows, (size_t)F * Sp))) return fail(rc);
-        if ((rc = dev_alloc(c, &c->d_snap, (size_t)c->dense_cap * A))) return fail(rc);
-    }
+    // (launch_detect); its buffers scale with the detection capacity — beyond 2 GB the per-detection kernel is used instead.
+    // Narrow arrays get them when the caller picks that path (mmw_set_detect_path, or MMW_K4_VARIANT=2 in the environment).
+    if ((A >= 32 || env_int("MMW_K4_VARIANT") == 2) && (rc = alloc_refft_buffers(c))) return fail(rc);
     const size_t result_bytes = kResultHeaderBytes + (size_t)c->dense_cap * sizeof(mmw_detection);
     if ((rc = dev_alloc(c, &c->d_result, result_bytes))) return fail(rc);
     c->d_header = reinterpret_cast<uint32_t *>(c->d_result);
@@ -403,8 +414,8 @@ int mmw_get_info(const mmw_ctx *c, mmw_info *info)
     const long long N = (long long)p.Sp * p.Cp * p.A, M = (long long)p.Sp * p.Cp;
     info->algorithmic_bytes_per_frame = 28 * N + 8 * M;
     info->workspace_bytes = (long long)c->workspace_bytes;
-    // K1, K2, K3, list, measure; the selective re-FFT path of wide arrays runs rows + extract + angle instead of measure
-    info->kernels_per_batch = (c->d_snap != nullptr && p.k4_variant != 1) ? 7 : 5;
+    // K1, K2, K3, list, measure; the selective re-FFT path runs rows + extract + angle instead of measure (launch_detect's rule)
+    info->kernels_per_batch = ((p.A >= 32 || p.k4_variant == 2) && !p.keep_cube && c->d_snap != nullptr && p.k4_variant != 1) ? 7 : 5;
     return MMW_OK;
 }
 
@@ -456,6 +467,28 @@ int mmw_set_graph_mode(mmw_ctx *c, int enable)
 {
     if (!c) { set_last_error("mmw_set_graph_mode: null context"); return MMW_ERR_ARG; }
     c->graph_on = enable ? 1 : 0;
+    return MMW_OK;
+}
+
+int mmw_set_detect_path(mmw_ctx *c, int path)
+{
+    if (!c) { set_last_error("mmw_set_detect_path: null context"); return MMW_ERR_ARG; }
+    if (path != MMW_DETECT_AUTO && path != MMW_DETECT_PER_CELL && path != MMW_DETECT_REFFT) {
+        set_last_error("mmw_set_detect_path: path must be MMW_DETECT_AUTO, _PER_CELL or _REFFT, got %d", path);
+        return MMW_ERR_ARG;
+    }
+    if (c->submitted) { set_last_error("mmw_set_detect_path: a submitted batch is pending; collect it with mmw_wait"); return MMW_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    if (path == MMW_DETECT_REFFT) {
+        CK(cudaStreamSynchronize(c->stream));
+        int rc = alloc_refft_buffers(c);
+        if (rc) return rc;
+    }
+    if (c->plan.k4_variant != path && c->graphs) {      // the captured launch sequences belong to the old path
+        CK(cudaStreamSynchronize(c->stream));
+        destroy_graphs(c);
+    }
+    c->plan.k4_variant = path;                           // 0 / 1 / 2: the launcher's own numbering (launch_detect)
     return MMW_OK;
 }
 

@@ -1207,7 +1207,7 @@ cudaError_t launch_detect(const PlanDev &p, const DetectBuffers &b, int n_frames
     const bool wide = p.A >= kMeasWideA;
     // wide arrays, fused mode: one more Doppler FFT of the rows that have hits, then the angle spectra as FFTs
     // (PlanDev.k4_variant = 1 keeps the per-detection kernel below: tests and profiles compare the two)
-    if (wide && !p.keep_cube && b.rows != nullptr && b.snap != nullptr && p.k4_variant != 1) {
+    if ((wide || p.k4_variant == 2) && !p.keep_cube && b.rows != nullptr && b.snap != nullptr && p.k4_variant != 1) {
         const int rgrid = (dense_cap + 255) / 256 < sm_count * 4 ? (dense_cap + 255) / 256 : sm_count * 4;
         rows_kernel<<<rgrid < 1 ? 1 : rgrid, 256, 0, st>>>(p, b.keys, b.offsets, b.rows, b.ticket + 2, n_frames, dense_cap);
         e = cudaGetLastError();

@@ -115,6 +115,21 @@ int mmw_set_frame_offset(mmw_ctx *ctx, uint32_t first_frame);
  * Off by default; results are identical either way. */
 int mmw_set_graph_mode(mmw_ctx *ctx, int enable);
 
+/* How the detection records get their antenna snapshots when the Doppler cube is not kept (fused mode).
+ * MMW_DETECT_PER_CELL: every detection re-derives its Doppler bin from the range spectrum, one DFT per detection per antenna
+ *   (detections of one range bin share the rows they read) — one kernel, the lowest latency for a few frames per call.
+ * MMW_DETECT_REFFT: every (frame, range bin) row that has a hit is Doppler-transformed once more by the FFT stage's own code
+ *   and the detected bins are picked out of it (snapshots bit-identical to what the cube would hold), then the angle spectra
+ *   are FFTs — three kernels, the cheaper path for large batches (256 x 128 x 4 x 1024 frames: 0.135 -> 0.08 ms).
+ * MMW_DETECT_AUTO (default): _REFFT for arrays of 32 antennas and more, _PER_CELL below.
+ * The two paths agree on everything but angle bins at near ties of the angle spectrum; a job that shards frames over
+ * several contexts must give all of them the same path to get byte-identical lists.  Call between batches.
+ * (The reference has no detection stage; acceleration.cu:518-523 picks one range peak on the host.) */
+#define MMW_DETECT_AUTO 0
+#define MMW_DETECT_PER_CELL 1
+#define MMW_DETECT_REFFT 2
+int mmw_set_detect_path(mmw_ctx *ctx, int path);
+
 /* The CUDA stream every call of this context runs on (a cudaStream_t). */
 void *mmw_stream(mmw_ctx *ctx);
 /* Run on a caller-owned stream instead (e.g. torch's current stream); NULL restores the context's own. */

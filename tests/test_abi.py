@@ -129,3 +129,15 @@ def test_product_does_not_import_oracle():
                 assert "oracle." not in txt.replace("oracle/_ref", "").replace("oracle/Makefile", "") or f == "build.py", f
                 assert "import oracle" not in txt and "from oracle" not in txt, f
                 assert "cufft" not in txt.lower() or "no cufft" in txt.lower(), f
+
+
+def test_detect_path_constants_match_the_header():
+    """MMW_DETECT_* of include/mmw_radar.h and the ctypes mirror's DETECT_* are the same numbers"""
+    import re
+
+    import __graft_entry__ as entry
+
+    pkg = entry.load_package()
+    hdr = open(os.path.join(ROOT, "include", "mmw_radar.h")).read()
+    vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define MMW_DETECT_(\w+) (\d+)", hdr)}
+    assert vals == {"AUTO": pkg.api.DETECT_AUTO, "PER_CELL": pkg.api.DETECT_PER_CELL, "REFFT": pkg.api.DETECT_REFFT}

@@ -147,13 +147,27 @@ def test_cfg3_bench_batch_with_cube(pkg, orc):
 
 
 def test_cfg2_bench_batch_sampled_frames(pkg, orc):
-    """cfg2 at the bench's 1024 frames per batch; the oracle checks two sampled frames"""
+    """cfg2 at the bench's 1024 frames per batch, on the detection path the bench selects for it (MMW_DETECT_REFFT: hit rows
+    re-transformed once, angle spectra as FFTs) and on the library's default for narrow arrays (a DFT per detection); the
+    oracle checks two sampled frames of each, and the two lists must agree on everything but angle bins at near ties"""
     S, C, A, F = 256, 128, 4, 1024
     adc = _torch_batch(pkg, F, S, C, A, cfg=2)
+    lists = {}
     with pkg.RadarContext(S, C, A, F, max_det_per_frame=4096) as ctx:
-        dets, overflow = ctx.process_host(adc, F)
-        assert not overflow
-        _check_frames(pkg, orc, ctx, dets, adc, [517, 1023], S, C, A, "cfg2 x1024")
+        for path, tag in ((pkg.api.DETECT_REFFT, "re-FFT"), (pkg.api.DETECT_PER_CELL, "per-cell")):
+            ctx.set_detect_path(path)
+            assert int(ctx.info.kernels_per_batch) == (7 if path == pkg.api.DETECT_REFFT else 5)
+            dets, overflow = ctx.process_host(adc, F)
+            assert not overflow
+            _check_frames(pkg, orc, ctx, dets, adc, [517, 1023], S, C, A, f"cfg2 x1024 {tag}")
+            lists[path] = dets.copy()
+    a, b = lists[pkg.api.DETECT_REFFT], lists[pkg.api.DETECT_PER_CELL]
+    assert len(a) == len(b)
+    for field in ("frame", "range_bin", "doppler_bin", "power", "noise", "flags"):
+        assert np.array_equal(a[field], b[field]), field
+    differ = int((a["angle_bin"] != b["angle_bin"]).sum())
+    print(f"\ncfg2 x1024: {len(a)} detections, angle bins differing between the two detection paths (near ties): {differ}")
+    assert differ <= len(a) // 1000 + 2
 
 
 def test_cfg5_sensor_cube_batch_and_single_calls(pkg, orc):

@@ -52,6 +52,12 @@ def test_no_kernel_writes_outside_its_buffers(pkg, guard_env, S, C, A, F, keep, 
         ctx.set_base_frame(adc[0])                                       # static-clutter removal: K1's BASE instantiation
         ctx.process_host(adc, F)
         ctx.set_base_frame(None)
+        if not keep:                                                     # the re-FFT detection path on narrow arrays too
+            ctx.set_detect_path(pkg.api.DETECT_REFFT)
+            ctx.process_host(adc, F)
+            ctx.set_detect_path(pkg.api.DETECT_PER_CELL)
+            ctx.process_host(adc, F)
+            ctx.set_detect_path(pkg.api.DETECT_AUTO)
         ctx.set_graph_mode(True)                                         # latency mode: one frame per call through a CUDA graph
         for f in range(min(F, 3)):
             ctx.process_host(adc[f:f + 1], 1)
