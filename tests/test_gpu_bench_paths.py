@@ -32,7 +32,7 @@ pytestmark = pytest.mark.gpu
 
 ALPHA = 15.0
 NEAR = 1e-5
-P_ATOL_OF_MAX = 2e-6            # measured on B200: 1.6e-7 .. 3.7e-7 (profiles/parity_r2.md)
+P_ATOL_OF_MAX = 2e-6            # measured on B200: 1.6e-7 .. 3.7e-7 (profiles/r2/parity_maxima_bench_paths.log: this file run with -s)
 P_RTOL_ABOVE_FLOOR = 1e-5       # measured: 2.4e-7 .. 7.0e-7; north_star allows 1e-4
 P_FLOOR_OF_MAX = 1e-3
 # The noise estimate is the mean of 248 power-map cells near the noise floor.  Its fp32 sum is add-only (~1e-6), but
