@@ -47,9 +47,6 @@ WORKLOADS = {
     "cfg5": dict(kind="stream", S=256, C=128, A=12, F=64, idx=4),
     "cfg1": dict(kind="legacy", S=100, C=128, A=4, F=4096, idx=0),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the workload's batch size, from the
-# committed `ncu --set full` captures (profiles/ncu_r1_stages_cfg3.md, _cfg2.md); None = no capture for that workload
-NCU_TRAFFIC_BYTES = {"cfg3": 1149854976, "cfg2": 1552098000, "cfg4": None, "cfg5": None, "cfg1": None}
 
 
 def peaks():
