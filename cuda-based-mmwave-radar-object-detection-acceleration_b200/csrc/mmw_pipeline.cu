@@ -1181,7 +1181,8 @@ cudaError_t launch_range_fft(const PlanDev &p, const int16_t *adc, float2 *rs, i
     // and 5.6-5.7 TB/s with 256-byte ones (profiles/membench_r1.txt).  256 points: 32-row tiles still fit two CTAs of 8 warps per SM
     // and measured 4.5 % faster than 16-row tiles with three CTAs of 4 warps (cfg2 0.293 -> 0.280 ms).  512 points: a 32-row tile
     // needs 203 KB, one CTA of 16 warps per SM, and loses more to the barrier between the passes than the stores gain (0.224 ->
-    // 0.238 ms).  MMW_K1_VARIANT = 5 / 6 force 32- / 16-row tiles (profiles/experiments/r1_k1_tile_height.log).
+    // 0.238 ms).  MMW_K1_VARIANT = 5 / 6 force 32- / 16-row tiles (profiles/experiments/r1_k1_tile_height.log).  Re-measured with tiles
+    // from the counter (profiles/r2/sweep_k1_tiles_dynamic.log): same ranking, 8-row tiles at 512 points (four CTAs of 4 warps) 0.225 vs 0.201 ms.
     case 256:
         if (p.k1_variant == 6) return run_range<256, 16, 16, 16, 4, true, 128, 0>(p, adc, rs, n_frames, st);
         return run_range<256, 16, 16, 32, 8, true, 128, 0, 1, 16, 4>(p, adc, rs, n_frames, st);
