@@ -382,8 +382,13 @@ def measure_chain(env, name, F, K, W, D, keep_cube=False, e2e_steps=None, share_
         gather_records = min(F * max_det, ((most * 3 // 2 + 1024) // 1024) * 1024)
         for ln in lanes:
             if env.exchange == "peer":
-                ln.gather = pkg.sharding.PeerDetectionGather(ln.ctx, dev, gather_records)
-            else:
+                try:
+                    ln.gather = pkg.sharding.PeerDetectionGather(ln.ctx, dev, gather_records)
+                except pkg.sharding.PeerExchangeUnavailable as e:   # raised on every rank at once: fall back together
+                    if rank == 0:
+                        print(f"bench.py: peer exchange unavailable ({e}); using the NCCL gather", file=sys.stderr)
+                    env.exchange = "nccl"
+            if env.exchange != "peer":
                 ln.gather = pkg.sharding.DetectionGather(ln.ctx, dev, gather_records, side=side)
     gather = lanes[0].gather
 

@@ -436,17 +436,30 @@ class PeerExchange:
     (include/mmw_radar.h).  `all_gather_bytes(b: bytes) -> list[bytes]` is the launcher's transport for the 64-byte handles."""
 
     def __init__(self, ctx: "RadarContext", rank: int, n_ranks: int, records_per_rank: int, all_gather_bytes, depth: int = 4):
+        """Never raises between the collective calls: a rank whose set-up fails (no peer access, no IPC between the ranks'
+        processes, ...) still takes part in the handle all-gather and reports the failure in `self.error` (None = connected),
+        so the launcher can agree on a fall-back with a reduction over the ranks instead of hanging in a barrier."""
         self._L = load()
         self.ctx, self.rank, self.n_ranks, self.records_per_rank = ctx, rank, n_ranks, records_per_rank
-        h = C.c_void_p()
-        _check(self._L.mmw_exchange_create(ctx._h, rank, n_ranks, records_per_rank, depth, C.byref(h)))
-        self._x = h
+        self._x, self.error = None, None
         mine = (C.c_ubyte * 64)()
-        _check(self._L.mmw_exchange_handle(self._x, mine))
-        everyone = all_gather_bytes(bytes(mine))
+        try:
+            if os.environ.get("MMW_EXCHANGE_FAIL_RANK") == str(rank):      # tests: this rank pretends it cannot set up
+                raise RadarError(MMW_ERR_STATE, "peer exchange disabled on this rank by MMW_EXCHANGE_FAIL_RANK")
+            h = C.c_void_p()
+            _check(self._L.mmw_exchange_create(ctx._h, rank, n_ranks, records_per_rank, depth, C.byref(h)))
+            self._x = h
+            _check(self._L.mmw_exchange_handle(self._x, mine))
+        except RadarError as e:
+            self.error = e
+        everyone = all_gather_bytes(bytes(mine))                           # collective: every rank gets here
         assert len(everyone) == n_ranks and all(len(b) == 64 for b in everyone)
-        blob = (C.c_ubyte * (64 * n_ranks)).from_buffer_copy(b"".join(everyone))
-        _check(self._L.mmw_exchange_connect(self._x, blob))
+        if self.error is None:
+            try:
+                blob = (C.c_ubyte * (64 * n_ranks)).from_buffer_copy(b"".join(everyone))
+                _check(self._L.mmw_exchange_connect(self._x, blob))
+            except RadarError as e:
+                self.error = e
 
     def close(self):
         if getattr(self, "_x", None):

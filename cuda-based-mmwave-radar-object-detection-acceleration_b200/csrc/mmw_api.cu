@@ -131,11 +131,14 @@ static int env_int(const char *name)
     return v ? atoi(v) : 0;
 }
 
+// A failed runtime call also parks its code in the runtime's per-thread "last error", where the launchers' cudaGetLastError()
+// would find it after the NEXT (successful) kernel launch: it is cleared here, once it has been reported.
 #define CK(call)                                                                                          \
     do {                                                                                                  \
         cudaError_t e_ = (call);                                                                          \
         if (e_ != cudaSuccess) {                                                                          \
             set_last_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            (void)cudaGetLastError();                                                                     \
             return MMW_ERR_CUDA;                                                                          \
         }                                                                                                 \
     } while (0)

@@ -497,6 +497,7 @@ constexpr int kSmemBytes = (kN + kN / 32) * 8;
         cudaError_t e_ = (call);                                                                          \
         if (e_ != cudaSuccess) {                                                                          \
             mmw::set_last_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            (void)cudaGetLastError();   /* reported: do not leave it for the next launch's check */       \
             return e_;                                                                                    \
         }                                                                                                 \
     } while (0)

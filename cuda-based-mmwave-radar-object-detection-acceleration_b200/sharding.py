@@ -168,6 +168,10 @@ class DetectionGather:
         return np.frombuffer(m[32:32 + REC_BYTES * n].tobytes(), dtype=det_dtype), header
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """mmw_exchange_* could not be set up on at least one rank (raised on every rank of the group at once)"""
+
+
 class PeerDetectionGather:
     """The exchange step without a kernel on the data path (mmw_exchange_*, include/mmw_radar.h): every rank's result block
     goes straight into rank 0's memory over NVLink by a copy-engine put, flags and credits are stream memory operations, and
@@ -191,9 +195,15 @@ class PeerDetectionGather:
             return [bytes(t.cpu().tolist()) for t in everyone]
 
         self.x = PeerExchange(ctx, self.rank, self.world, records_per_rank, all_gather_bytes, depth=depth)
+        # every rank is connected before the first put - or none uses the exchange: the reduction is the barrier
+        ok = torch.tensor([0 if self.x.error is not None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            why = str(self.x.error) if self.x.error is not None else "another rank could not set the exchange up"
+            self.x.close()
+            raise PeerExchangeUnavailable(why)                     # raised on EVERY rank: the caller falls back collectively
         self.merged_bytes = 32 + REC_BYTES * self.world * records_per_rank
         self.latest = None
-        dist.barrier(group=group)                                  # every rank is connected before the first put
 
     def run(self):
         self.x.put()

@@ -1,6 +1,7 @@
 """Worker of tests/test_gpu_multi.py: run under torchrun with one rank per GPU.  Every rank processes its contiguous
 frame block of the same seeded batch, the detection lists are gathered to rank 0 — argv[1] = "nccl": sharding.DetectionGather
-(NCCL gather + merge kernel), "peer": sharding.PeerDetectionGather (copy-engine puts into rank 0's memory, mmw_exchange_*) —
+(NCCL gather + merge kernel), "peer": sharding.PeerDetectionGather (copy-engine puts into rank 0's memory, mmw_exchange_*),
+"peer-fallback": the peer exchange refused by one rank, all ranks falling back to the NCCL gather together —
 over several pipelined steps (more than the exchange's ring depth), and rank 0 compares the merged list with the list one
 GPU computes for the whole batch.  Exit code 0 = byte-identical."""
 import faulthandler
@@ -33,7 +34,15 @@ def main():
     ctx.use_stream(stream.cuda_stream)
     mine = torch.from_numpy(adc[first:first + cnt]).to(dev)
     mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
-    gather = pkg.sharding.PeerDetectionGather(ctx, dev, 2048) if mode == "peer" else pkg.sharding.DetectionGather(ctx, dev, 2048)
+    if mode == "peer-fallback":                                   # one rank cannot set the peer exchange up: every rank must see
+        os.environ["MMW_EXCHANGE_FAIL_RANK"] = str(world - 1)     # PeerExchangeUnavailable and switch to the NCCL gather together
+        try:
+            pkg.sharding.PeerDetectionGather(ctx, dev, 2048)
+            raise SystemExit("the peer exchange came up although a rank refused it")
+        except pkg.sharding.PeerExchangeUnavailable:
+            gather = pkg.sharding.DetectionGather(ctx, dev, 2048)
+    else:
+        gather = pkg.sharding.PeerDetectionGather(ctx, dev, 2048) if mode == "peer" else pkg.sharding.DetectionGather(ctx, dev, 2048)
     with torch.cuda.stream(stream):
         for _ in range(11):                                       # several steps: exercises the double buffering / the slot ring
             ctx.process_device(mine, cnt)

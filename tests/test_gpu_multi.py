@@ -11,9 +11,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["nccl", "peer"])
+@pytest.mark.parametrize("mode", ["nccl", "peer", "peer-fallback"])
 def test_gather_equals_single_gpu(mode):
-    """nccl: NCCL gather per step; peer: copy-engine puts into rank 0's memory (mmw_exchange_*), NCCL for the set-up only"""
+    """nccl: NCCL gather per step; peer: copy-engine puts into rank 0's memory (mmw_exchange_*), NCCL for the set-up only;
+    peer-fallback: one rank cannot set the peer exchange up, every rank learns it at once and uses the NCCL gather"""
     import torch
 
     n = torch.cuda.device_count()
@@ -21,7 +22,7 @@ def test_gather_equals_single_gpu(mode):
         pytest.skip("needs two GPUs")
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533" if mode == "nccl" else "29534", os.path.join(ROOT, "tests", "dist_gather_check.py"), mode]
+           "--master-port", {"nccl": "29533", "peer": "29534", "peer-fallback": "29535"}[mode], os.path.join(ROOT, "tests", "dist_gather_check.py"), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "match=True" in r.stdout
