@@ -1,6 +1,7 @@
 """Generates tests/golden/chain_numpy.npz: the north-star stages (window, range FFT, Doppler FFT, power map, 2-D CA-CFAR,
 angle arg-max, 3x3 grouping) computed with numpy alone — numpy.fft and brute-force window sums in fp64, no oracle code
-— on seeded synthetic cubes of the reference's own frame shape (100 samples x 128 chirps x 4 rx) and of 64 x 64 x 2.
+— on seeded synthetic cubes of the reference's own frame shape (100 samples x 128 chirps x 4 rx), of 64 x 64 x 2, of a
+192-antenna array (64 x 64 x 192) and of a ragged shape (68 x 66 x 3).
 
 The reference has no code, tests or vectors for these stages ("parity unpinned"); this fixture pins the
 definitions of DESIGN.md §2 independently of oracle/mmw_oracle.c, so that the oracle (tests/test_oracle_pin.py, no GPU)
@@ -20,7 +21,9 @@ import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
 GR, GD, TR, TD, ALPHA = 2, 2, 8, 4, 15.0
-CASES = [(100, 128, 4, 2, 21), (64, 64, 2, 2, 22)]          # S, C, A, frames, synth cfg
+# S, C, A, frames, synth cfg: the reference's frame shape, a small square cube, a wide array (A > 64: the 256-point angle FFT of
+# the imaging configuration) and a ragged shape zero-padded on both axes (68 -> 128 samples, 66 -> 128 chirps)
+CASES = [(100, 128, 4, 2, 21), (64, 64, 2, 2, 22), (64, 64, 192, 1, 23), (68, 66, 3, 1, 24)]
 
 
 def next_pow2(n):
