@@ -35,5 +35,7 @@ def test_reference_arm_chain_workload_and_nonzero_ranks_stay_silent():
     d = json.loads(_run(["--workload", "cfg2", "--steps", "1", "--warmup", "0"]).strip())
     assert KEYS <= set(d) and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert "256 samples x 128 chirps x 4 antennas" in d["config"]["workload"]
+    # the GPU arm's workload keys under the GPU arm's names (the bounded CPU sample is named separately)
+    assert d["config"]["frames_per_gpu_per_step"] == 1024 and d["config"]["sample_frames_per_step"] > 0
     # under torchrun only rank 0 works and prints
     assert _run(["--workload", "cfg2", "--steps", "1", "--warmup", "0"], env={"RANK": "1", "WORLD_SIZE": "2"}).strip() == ""
