@@ -110,3 +110,54 @@ def test_guard_check_needs_the_switch(pkg):
     with pkg.RadarContext(128, 64, 4, 1) as ctx:
         with pytest.raises(Exception):
             ctx.check_guards()
+
+
+def test_repeated_runs_under_contention_give_the_same_bytes(pkg):
+    """A race check by repetition (racecheck is part of the closed compute-sanitizer): three contexts on three streams run
+    the same batch at the same time, twenty rounds, so the persistent FFT kernels, their tile counters and the in-place
+    warp-private Doppler passes of different batches share the SMs in ever different interleavings — every round of every
+    context must return the bytes of a context running alone, power map included."""
+    import torch
+
+    S, C, A, F = 512, 256, 12, 8
+    adc = pkg.synth.cube_batch(F, S, C, A, cfg=3, n_targets=8)
+    dev = torch.from_numpy(adc).cuda()
+    with pkg.RadarContext(S, C, A, F, max_det_per_frame=2048) as alone:
+        want, _ = alone.process_host(adc, F)
+        want = want.copy()
+        pmap = alone.power_map(F - 1).copy()
+    ctxs = [pkg.RadarContext(S, C, A, F, max_det_per_frame=2048) for _ in range(3)]
+    streams = [torch.cuda.Stream() for _ in ctxs]
+    try:
+        for c, s in zip(ctxs, streams):
+            c.use_stream(s.cuda_stream)
+        for rnd in range(20):
+            for c in ctxs:                                   # queued back to back: the three batches overlap on the device
+                c.process_device(dev, F)
+            for i, c in enumerate(ctxs):
+                got, _ = c.read_detections()
+                assert got.tobytes() == want.tobytes(), f"round {rnd}, context {i}: detection list differs"
+            if rnd % 5 == 0:
+                assert np.array_equal(ctxs[rnd % 3].power_map(F - 1), pmap)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("kernel", [2, 1])
+def test_legacy_kernels_repeat_bit_for_bit(pkg, kernel):
+    """the 8-CTA cluster kernel (DSMEM exchange, cluster barriers) and the one-CTA kernel, 200 calls on the same frame: the
+    same raw bin and the same spectrum bytes every time"""
+    cap = pkg.synth.legacy_capture(2, seed=5)
+    base = np.zeros(12800, np.complex128)
+    pkg.api.legacy_configure(kernel_variant=kernel, quiet=1)
+    try:
+        d0, raw0 = pkg.api.legacy_process_frame(cap[1], base)
+        spec0 = pkg.api.legacy_spectrum().tobytes()
+        for i in range(200):
+            d, raw = pkg.api.legacy_process_frame(cap[1], base)
+            assert (d, raw) == (d0, raw0)
+            if i % 20 == 0:
+                assert pkg.api.legacy_spectrum().tobytes() == spec0
+    finally:
+        pkg.api.legacy_configure(kernel_variant=0)
