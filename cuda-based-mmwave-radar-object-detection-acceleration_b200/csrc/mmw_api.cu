@@ -597,8 +597,7 @@ static int run_batch_graphed(mmw_ctx *c, const int16_t *adc_dev, int n_frames)
             set_last_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
             return MMW_ERR_CUDA;
         }
-        mmw_ctx::GraphEntry ge;
-        memset(&ge, 0, sizeof(ge));
+        mmw_ctx::GraphEntry ge{};
         ge.graph = graph; ge.exec = exec; ge.frame_offset = c->plan.frame_offset;
         // the node that writes mmw_detection.frame: the only consumer of PlanDev.frame_offset
         size_t n_nodes = 0;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kCfarNT) cfar_kernel(PlanDev p, const float *_
     float *ringS = fullS + th_ * RS;                     // [th_][RS]
     uint32_t *words = reinterpret_cast<uint32_t *>(ringS + th_ * RS);   // [RT]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int r0 = blockIdx.x * kCfarRT;
     const int dblk = blockIdx.y;
     const int f = blockIdx.z;
