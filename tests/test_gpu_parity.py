@@ -408,3 +408,29 @@ def test_chain_matches_numpy_golden_fixture(pkg, golden_dir):
                         assert rec["angle_bin"] == ab
                     n_checked += 1
                 assert n_checked > 0
+
+
+@pytest.mark.parametrize("shape,variants", [((512, 256, 12), [1, 6, 10, 12, 13, 14, 15, 16, 17]), ((256, 128, 4), [1, 6, 11]),
+                                            ((500, 130, 2), [10, 13, 17])])
+def test_doppler_kernel_forms_give_the_same_bits(pkg, shape, variants, monkeypatch):
+    """Every selectable form of K2 (MMW_K2_VARIANT, the shapes profiles/sweep_env.py compares: CTA-shared tiles of other
+    heights / in place with three buffers, warp-private tiles with 5-12 warps, two or three staging buffers, two to four CTAs
+    per SM, and the 128-point warp-private form) runs the same arithmetic in the same order, so its power maps and detection
+    lists must equal the default form's byte for byte — on a full-length shape, a 128-point shape and a chirp-padded one
+    (130 -> 256 chirps: the PAD instantiations, rows staged at a stride of C elements)."""
+    S, C, A = shape
+    F = 5                                                    # several tiles per warp and a ragged tail
+    adc = pkg.synth.cube_batch(F, S, C, A, cfg=3, n_targets=6)
+    monkeypatch.delenv("MMW_K2_VARIANT", raising=False)
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        want, _ = ctx.process_host(adc, F)
+        want = want.copy()
+        pmaps = [ctx.power_map(f).copy() for f in range(F)]
+    assert len(want) > 0
+    for v in variants:
+        monkeypatch.setenv("MMW_K2_VARIANT", str(v))
+        with pkg.RadarContext(S, C, A, F) as ctx:
+            got, _ = ctx.process_host(adc, F)
+            for f in range(F):
+                assert np.array_equal(ctx.power_map(f), pmaps[f]), f"K2 variant {v}: power map of frame {f} differs"
+            assert got.tobytes() == want.tobytes(), f"K2 variant {v}: detection list differs"
