@@ -434,3 +434,30 @@ def test_doppler_kernel_forms_give_the_same_bits(pkg, shape, variants, monkeypat
             for f in range(F):
                 assert np.array_equal(ctx.power_map(f), pmaps[f]), f"K2 variant {v}: power map of frame {f} differs"
             assert got.tobytes() == want.tobytes(), f"K2 variant {v}: detection list differs"
+
+
+@pytest.mark.parametrize("shape,variant", [((512, 256, 12), 5), ((256, 128, 4), 6), ((1024, 64, 2), 6), ((500, 130, 2), 5)])
+def test_range_kernel_forms_give_the_same_bits(pkg, shape, variant, monkeypatch):
+    """The other tile heights of K1 (MMW_K1_VARIANT: 32-row tiles at 512 points, 16-row tiles at 256, 8-row tiles at 1024) and
+    both ways of handing tiles out (MMW_SCHED: counter or fixed stride) compute every chirp's transform with the same
+    arithmetic: range spectra, power maps and lists must equal the default's byte for byte."""
+    S, C, A = shape
+    F = 3
+    adc = pkg.synth.cube_batch(F, S, C, A, cfg=3, n_targets=6)
+    for name in ("MMW_K1_VARIANT", "MMW_SCHED"):
+        monkeypatch.delenv(name, raising=False)
+    with pkg.RadarContext(S, C, A, F) as ctx:
+        want, _ = ctx.process_host(adc, F)
+        want = want.copy()
+        rs = ctx.range_spectrum(F - 1).copy()
+        pm = ctx.power_map(F - 1).copy()
+    for env in ({"MMW_K1_VARIANT": str(variant)}, {"MMW_SCHED": "0"}, {"MMW_SCHED": "3"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with pkg.RadarContext(S, C, A, F) as ctx:
+            got, _ = ctx.process_host(adc, F)
+            assert np.array_equal(ctx.range_spectrum(F - 1), rs), f"{env}: range spectrum differs"
+            assert np.array_equal(ctx.power_map(F - 1), pm), f"{env}: power map differs"
+            assert got.tobytes() == want.tobytes(), f"{env}: detection list differs"
+        for k in env:
+            monkeypatch.delenv(k)
