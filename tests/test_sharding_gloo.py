@@ -78,3 +78,16 @@ def test_gather_equals_single_rank(world, n_frames):
     adc = pkg.synth.cube_batch(n_frames, S, C, A, cfg=4, n_targets=2)
     want = orc.process_frames(adc, n_frames, S, C, A, orc.hann_periodic(S), orc.hann_periodic(C))["dets"]
     assert len(want) > 0 and got.tobytes() == want.tobytes()      # byte-identical to the 1-rank list
+
+
+def test_c_abi_shard_rule_is_the_python_rule():
+    """mmw_shard_frames (the rule mmw_group_* uses inside the library) and sharding.shard_frames (the torchrun launchers' rule)
+    are the same function: contiguous blocks, remainders to the low ranks — pure host code, no GPU"""
+    import __graft_entry__ as entry
+
+    pkg = entry.load_package()
+    for n in (0, 1, 7, 11, 64, 1000, 4097):
+        for w in (1, 2, 3, 5, 8):
+            spans = [pkg.api.shard_frames(n, w, r) for r in range(w)]
+            assert spans == [pkg.sharding.shard_frames(n, w, r) for r in range(w)]
+            assert sum(c for _, c in spans) == n and all(spans[r][0] + spans[r][1] == spans[r + 1][0] for r in range(w - 1))
